@@ -1,0 +1,94 @@
+"""CPU tests: the oracle against the committed golden vectors (tests/golden/, made by make_golden.py from the
+reference's own NumPy transformer / Aux_M* literals / cv2.getPerspectiveTransform) and against itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from unsuperviseddeephomographyral2018_b200 import params as P
+
+
+def test_dlt_matches_reference_aux_and_cv2(golden_dir):
+    g = np.load(os.path.join(golden_dir, "dlt_golden.npz"))
+    pts1, h4p = torch.tensor(g["pts1"]), torch.tensor(g["h4p"])
+    A, b = O.dlt_system(pts1, pts1 + h4p)
+    assert np.array_equal(A.numpy(), g["A_ref"]) and np.array_equal(b.numpy(), g["b_ref"])
+    assert (A[:, 0, 0] == 0).all()                      # pivoting is mandatory
+    H = O.solve_dlt(pts1, h4p).numpy()
+    assert np.abs(H - g["H_ref"]).max() < 1e-9
+    assert np.abs(H[:16] - g["H_cv2"]).max() < 1e-9
+    # fp32 restatement stays close to fp64 (reference arithmetic is fp32)
+    H32 = O.solve_dlt(pts1.float(), h4p.float()).double().numpy()
+    assert np.abs(H32 - g["H_ref"]).max() / np.abs(g["H_ref"]).max() < 1e-4
+    # H maps pts1 -> pts2
+    p = torch.cat([pts1.reshape(-1, 4, 2), torch.ones(32, 4, 1, dtype=torch.float64)], 2)
+    q = torch.einsum("bij,bkj->bki", torch.tensor(H), p)
+    assert (q[..., :2] / q[..., 2:] - (pts1 + h4p).reshape(-1, 4, 2)).abs().max() < 1e-8
+
+
+def test_warp_matches_reference_numpy_twin(golden_dir):
+    g = np.load(os.path.join(golden_dir, "warp_golden.npz"))
+    out, cond = O.transformer(torch.tensor(g["small_img"]), torch.tensor(g["small_theta"]), (24, 32))
+    assert np.abs(out.numpy() - g["small_out"]).max() < 1e-9
+    assert (np.abs(g["small_out"]) < 1e-9).mean() > 0.01          # the set does exercise out-of-range (~0) samples
+    batch = O.make_batch(int(g["full_seed"]), 2, dtype=torch.float64)
+    assert int(batch["I_u8"].astype(np.int64).sum()) == int(g["full_I_u8_crc"]), "synthetic input generator drifted"
+    win = O.transform(batch["I_aug"], batch["H_gt"], batch["patch_indices"], 128).numpy()[..., 0]
+    assert np.abs(win - g["full_window"]).max() < 1e-9
+    cf = O.warp_closed_form(batch["I_aug"], batch["H_gt"], batch["pts1"][:, 0].numpy(), batch["pts1"][:, 1].numpy(), 128, 128)
+    assert np.abs(cf.numpy()[..., 0] - g["full_window"]).max() < 1e-4
+
+
+def test_warp_with_gt_homography_reproduces_I2():
+    """End-to-end chain of SURVEY §8a-W: DLT(pts1, gt) -> warp -> window == I2 patch up to the uint8 cast of I'."""
+    batch = O.make_batch(3, 2)
+    H = O.solve_dlt(batch["pts1"], batch["gt"])
+    pred = O.transform(batch["I_aug"], H, batch["patch_indices"], 128)
+    d = (pred - batch["I2_aug"]).abs()
+    assert d.mean() < 1.0 / 69.0                                     # < 1 grey level after normalisation
+
+
+def test_e2e_golden_regression(golden_dir):
+    g = np.load(os.path.join(golden_dir, "e2e_golden.npz"))
+    specs = P.param_specs()
+    assert P.num_parameters(specs) == 34192264
+    for seed in (0, 1):
+        flat = torch.tensor(P.init_flat(seed))
+        batch = O.make_batch(seed, 2)
+        dig = np.array([batch["I_aug"].double().sum().item(), batch["I2_aug"].double().sum().item(),
+                        batch["pts1"].double().sum().item(), batch["gt"].double().sum().item()])
+        assert np.allclose(dig, g["s%d_input_digest" % seed], rtol=1e-12)
+        out = O.forward(P.unflatten(flat, specs), batch, None, mode="test")
+        for k in ("pred_h4p", "H_mat", "h_loss", "l1_loss", "rec_loss", "ssim_loss", "l1_smooth_loss", "ncc_loss",
+                  "bounded_h_loss", "num_fail"):
+            ref = g["s%d_%s" % (seed, k)]
+            assert np.allclose(out[k].detach().numpy(), ref, rtol=2e-4, atol=2e-5), k
+        assert np.abs(out["pred_I2"].detach().numpy() - g["s%d_pred_I2" % seed]).max() < 1e-3
+
+
+def test_schedule_and_adam():
+    assert O.decay_steps(1e-4, 0.9e-4) == 58117 and O.decay_steps(5e-4, 0.9e-4) == 3570
+    assert O.learning_rate(58116, 1e-4, 0.9e-4) == 1e-4
+    assert abs(O.learning_rate(58117, 1e-4, 0.9e-4) - 0.96e-4) < 1e-18
+    p, g = torch.tensor([1.0, -2.0]), torch.tensor([0.5, -0.25])
+    p1, m, v = O.adam_step(p, g, torch.zeros(2), torch.zeros(2), 1, 1e-3)
+    # first TF-Adam step moves every coordinate by ~lr against the gradient sign
+    assert torch.allclose(p1, p - 1e-3 * torch.sign(g), atol=1e-6)
+
+
+def test_fp64_gradient_chain():
+    """DLT -> warp -> L1 is differentiable w.r.t. h4p and agrees with central differences."""
+    batch = O.make_batch(5, 1, dtype=torch.float64)
+    h = (batch["gt"] + 0.37).clone().requires_grad_(True)
+
+    def f(hh):
+        Hm = O.solve_dlt(batch["pts1"], hh)
+        return (O.transform(batch["I_aug"], Hm, batch["patch_indices"], 128) - batch["I2_aug"]).abs().mean()
+    f(h).backward()
+    num = torch.zeros(8, dtype=torch.float64)
+    for i in range(8):
+        e = torch.zeros(1, 8, dtype=torch.float64); e[0, i] = 1e-5
+        num[i] = (f(h.detach() + e) - f(h.detach() - e)) / 2e-5
+    assert (h.grad[0] - num).abs().max() / num.abs().max() < 1e-4
