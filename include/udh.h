@@ -1,0 +1,147 @@
+/*
+ * libudh.so — C ABI of the B200-native unsupervised-deep-homography hot path.
+ *
+ * The reference (tynguyen/unsupervisedDeepHomographyRAL2018) is a pure-Python TF1 graph and has no FFI of its
+ * own; each entry point below replaces the group of TF ops cited next to it (file:line under /root/reference/code).
+ * The Python mirror of the reference API (HomographyModel, transformer, the CLI) sits on top of this ABI and is
+ * the binding a maintainer would use.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name says `host`; the library never
+ *     allocates device memory — scratch is passed in as a workspace sized by the *_workspace_bytes query;
+ *   - tensors are dense NHWC fp32 (the reference's layout and dtype); indices are int32;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed as void*) and re-entrant across
+ *     streams; no exceptions cross the boundary: return 0 on success, a negative UDH_E* code otherwise and
+ *     udh_last_error() gives the message (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns UDH_ECUDA.
+ */
+#ifndef UDH_H_
+#define UDH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDH_OK 0
+#define UDH_EINVAL (-1) /* bad argument (shape, alignment, null pointer)   */
+#define UDH_ECUDA (-2)  /* CUDA runtime / launch error                      */
+#define UDH_ENOSUP (-3) /* configuration not supported by this build        */
+#define UDH_EWS (-4)    /* workspace too small                              */
+
+/* numeric mode of the regressor (udh_cnn_*).  FP32: CUDA-core fp32 everywhere — the parity mode.
+ * BF16: tcgen05 bf16 tensor-core tiles with fp32 TMEM accumulation, fp32 master weights — the throughput mode. */
+#define UDH_NUMERIC_FP32 0
+#define UDH_NUMERIC_BF16 1
+
+/* photometric loss selector for udh_warp_loss_bwd (reference --loss_type, homography_CNN_synthetic.py:51) */
+#define UDH_LOSS_L1 0        /* homography_model.py:328 */
+#define UDH_LOSS_REC 1       /* homography_model.py:303 */
+#define UDH_LOSS_L1_SMOOTH 2 /* homography_model.py:136-139,340 */
+
+/* slots of the `sums` accumulator (double[UDH_NSUMS]) filled by udh_warp_loss_fwd / udh_ssim_fwd */
+#define UDH_SUM_ABS 0   /* sum |pred - I2|            */
+#define UDH_SUM_SQ 1    /* sum (pred - I2)^2          */
+#define UDH_SUM_HUBER 2 /* sum huber_1(pred - I2)     */
+#define UDH_SUM_XY 3    /* sum pred * I2              */
+#define UDH_SUM_XX 4    /* sum pred^2                 */
+#define UDH_SUM_YY 5    /* sum I2^2                   */
+#define UDH_SUM_SSIM 6  /* sum clip((1-SSIM)/2,0,1)   */
+#define UDH_NSUMS 8
+
+/* slots of the float[UDH_NLOSSES] written by udh_photo_losses_finalize (homography_model.py:291-296) */
+#define UDH_L_REC 0
+#define UDH_L_SSIM 1
+#define UDH_L_L1 2
+#define UDH_L_L1_SMOOTH 3
+#define UDH_L_NCC 4
+#define UDH_NLOSSES 8
+
+/* slots of the float[UDH_NMETRICS] written by udh_h4p_loss (homography_model.py:274-281,288) */
+#define UDH_M_H_LOSS 0         /* sqrt(mean_{B x 8} (pred-gt)^2)                       */
+#define UDH_M_BOUNDED_H_LOSS 1 /* mean_b of per-sample RMSE, identity-bounded          */
+#define UDH_M_NUM_FAIL 2       /* #samples with RMSE >= identity RMSE                  */
+#define UDH_M_ACE 3            /* mean Euclidean corner distance (literature's metric) */
+#define UDH_NMETRICS 4
+
+int udh_version(void);
+const char* udh_last_error(void);
+/* 1 when a CUDA device is usable from this process, 0 otherwise (never throws). */
+int udh_device_available(void);
+
+/* ---- Row D: HomographyModel.solve_DLT (homography_model.py:169-250, utils/utils.py:11-122) ------------------
+ * pts1[B,8] (x,y)x[TL,TR,BR,BL], h4p[B,8] -> H[B,9] row-major, h33 = 1, mapping pts1 -> pts1+h4p in pixels.
+ * One warp per sample: 8x8 [A|b] in registers, LU with partial pivoting through warp shuffles
+ * (replaces the 8 tf.matmul with Aux_M*, stack/transpose and tf.matrix_solve at :223-242). */
+int udh_dlt_fwd(const float* pts1, const float* h4p, float* H, int B, void* stream);
+/* TF autodiff of the above: dH[B,9] -> dh4p[B,8] (solve A^T lambda = dH[0:8]; dA = -lambda h^T, db = lambda). */
+int udh_dlt_bwd(const float* pts1, const float* h4p, const float* H, const float* dH, float* dh4p, int B, void* stream);
+
+/* ---- Row W+L: HomographyModel.transform + photometric losses ----------------------------------------------
+ * (homography_model.py:252-269,291-296,328; utils/tf_spatial_transformer.py:76-247)
+ * Fused: H' = M^-1 H M, homography warp of I[B,img_h,img_w,C] (C in {1,3}), channel mean, and ONLY the window
+ * the reference gathers with patch_indices (a pw x ph rectangle whose first index patch_indices[b*idx_stride]
+ * = y0*img_w + x0 gives its origin; patch_indices == NULL means origin (0,0)), compared with I2[B,ph,pw].
+ * pred (nullable) receives pred_I2[B,ph,pw]; sums (double[UDH_NSUMS], caller-zeroed) accumulates the
+ * reductions every photometric loss needs.  pw must be a multiple of 4. */
+int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                      const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, float* pred, double* sums,
+                      int B, void* stream);
+/* d loss / d H [B,9] for loss_type in UDH_LOSS_*; `sums` is the forward accumulator (needed by REC),
+ * upstream multiplies the gradient (1.0 for a plain backward).  Recomputes the warp; no image-sized
+ * intermediates.  scratch: float[B*9], caller-provided. */
+int udh_warp_loss_bwd(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                      const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, int loss_type,
+                      const double* sums, float upstream, float* dH, float* scratch, int B, void* stream);
+/* SSIM diagnostic (homography_model.py:141-158): adds sum over the VALID 3x3 grid into sums[UDH_SUM_SSIM]. */
+int udh_ssim_fwd(const float* pred, const float* I2, int pw, int ph, double* sums, int B, void* stream);
+/* losses[UDH_NLOSSES] from sums; n = B*ph*pw, n_ssim = B*(ph-2)*(pw-2). */
+int udh_photo_losses_finalize(const double* sums, double n, double n_ssim, float* losses, void* stream);
+
+/* ---- the `transformer` operator (utils/tf_spatial_transformer.py:18,249-251) --------------------------------
+ * U[B,H,W,C], theta[B,9] (normalised homography H'), -> out[B,out_h,out_w,C]; reference semantics including
+ * the linspace grid, the t_s epsilon rule and clip-then-weight bilinear sampling. */
+int udh_transformer_fwd(const float* U, const float* theta, float* out, int B, int H, int W, int C, int out_h,
+                        int out_w, void* stream);
+
+/* ---- Row L (h4p part): h_loss and the test-mode metrics (homography_model.py:274-281,288) -------------------
+ * metrics: float[UDH_NMETRICS]; per_sample (nullable): float[B] batch_h_loss; dpred (nullable): d h_loss / d pred. */
+int udh_h4p_loss(const float* pred, const float* gt, int B, float* metrics, float* per_sample, float* dpred,
+                 void* stream);
+
+/* ---- Row C: HomographyModel._vgg (homography_model.py:88-133) -----------------------------------------------
+ * params / grads: the flat fp32 buffer laid out by udh_param_offset (TF-Slim checkpoint shapes: HWIO conv
+ * kernels, [in,out] fc kernels, NHWC flatten).  I1, I2: [B,P,P] gray patches (the two channels of model_input,
+ * homography_model.py:359, read in place — no concat copy).  train != 0 enables dropout(keep 0.5) after conv4_2
+ * and fc1 with masks drawn from `seed` (kept in the workspace for the backward and readable with
+ * udh_cnn_dropout_masks).  The workspace keeps the activations between fwd and bwd. */
+size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode);
+int udh_cnn_fwd(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes, int B,
+                int P, int train, uint64_t seed, int numeric_mode, void* stream);
+/* dh4p[B,8] -> grads (ACCUMULATED into the flat buffer: caller zeroes it once per step). */
+int udh_cnn_bwd(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
+                size_t ws_bytes, int B, int P, int train, int numeric_mode, void* stream);
+/* device pointers (inside ws) of the uint8 keep-masks of the last train-mode forward: [B,(P/8)^2*128] and [B,1024]. */
+int udh_cnn_dropout_masks(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, const uint8_t** mask_conv4,
+                          const uint8_t** mask_fc1);
+/* device pointer (inside ws) of a saved activation, for tests: layer 0..7 = conv outputs, 8..10 = pool1..3,
+ * 11 = fc1 (post-ReLU, pre-dropout).  *numel receives the element count. */
+int udh_cnn_activation(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, int layer, const float** ptr,
+                       size_t* numel);
+/* layout of the flat parameter buffer: tensor index 0..19 = (conv w, conv b) x 8, fc1 w, fc1 b, fc2 w, fc2 b. */
+int udh_param_offset(int P, int tensor, size_t* offset_floats, size_t* numel);
+size_t udh_param_total_floats(int P);
+
+/* ---- Row O: TF-1 Adam (homography_CNN_synthetic.py:183,278) --------------------------------------------------
+ * g' = g * grad_scale (1/world_size folds get_average_grads, utils/utils.py:380-403, into the update);
+ * m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= alpha_t * m / (sqrt(v) + eps), alpha_t = lr_t*sqrt(1-b2^t)/(1-b1^t)
+ * computed by the caller (t is 1-based).  If zero_grad != 0 the gradient buffer is cleared in the same pass. */
+int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                  float eps, float grad_scale, int zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDH_H_ */

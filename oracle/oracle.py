@@ -137,7 +137,7 @@ def norm_matrices(img_w, img_h, dtype):
     return torch.tensor(M, dtype=dtype), torch.tensor(M_inv.astype(np.float32), dtype=dtype)
 
 
-def transform(I, H_mat, patch_indices, patch_size):
+def transform(I, H_mat, patch_indices, patch_size, patch_w=None):
     """homography_model.py:252-269: H' = M^-1 H M, full-grid warp of I [B,Hh,W,C], channel mean,
     flat gather of `patch_indices` [B,P*P] (+ b*Hh*W, :74-76) -> pred_I2 [B,P,P,1]."""
     B, Hh, W, C = I.shape
@@ -146,7 +146,7 @@ def transform(I, H_mat, patch_indices, patch_size):
     warped, _ = transformer(I, Hn, (Hh, W))                                              # :257
     gray = warped.mean(dim=3).reshape(-1)                                                # :263-264
     idx = patch_indices.reshape(B, -1).to(torch.int64) + (torch.arange(B, dtype=torch.int64) * (Hh * W)).unsqueeze(1)
-    return gray[idx.reshape(-1)].reshape(B, patch_size, patch_size, 1)                  # :267-269
+    return gray[idx.reshape(-1)].reshape(B, patch_size, patch_w or patch_size, 1)       # :267-269
 
 
 def warp_closed_form(I, H_mat, x0, y0, pw, ph):

@@ -1,0 +1,302 @@
+"""GPU parity tests (-m gpu): libudh's CUDA path, called through the C ABI, against the CPU oracle and the committed
+golden vectors (tests/golden/, produced from the reference's own NumPy transformer / Aux_M* / cv2).
+
+Tolerances (floating point; the reference computes in fp32):
+  DLT H            : |dH| <= 2e-4 * max|H| against the fp64 golden (fp32 LU of a cond~5e5 system)
+  warp pred_I2     : |d| <= 2e-4 abs on >= 99.9 % of pixels (bilinear of unit-variance data, fp32 coordinates of
+                     magnitude ~300 px; isolated pixels that straddle a clip boundary may differ), mean |d| <= 2e-5
+  photometric loss : 1e-4 relative
+  CNN pred_h4p     : 2e-4 abs (fp32 mode)
+  gradients        : relative L2 error <= 2e-3 per tensor (fp32 atomics, different summation order)
+  mean corner error: |MCE_cuda - MCE_oracle| <= 1e-3 px  (BASELINE.json north_star)
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O                                               # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def udh():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import unsuperviseddeephomographyral2018_b200 as pkg
+    from unsuperviseddeephomographyral2018_b200 import _lib, engine, ops, params
+    _lib.require_device()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.lib, ns.ops, ns.engine, ns.params, ns.pkg = _lib, ops, engine, params, pkg
+    return ns
+
+
+def dev(batch):
+    return {k: (v.cuda().contiguous() if isinstance(v, torch.Tensor) else v) for k, v in batch.items()}
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+# ------------------------------------------------------------------------------------------------ DLT
+def test_dlt_forward_golden(udh, golden_dir):
+    g = np.load(os.path.join(golden_dir, "dlt_golden.npz"))
+    pts1 = torch.tensor(g["pts1"], dtype=torch.float32).cuda()
+    h4p = torch.tensor(g["h4p"], dtype=torch.float32).cuda()
+    H = udh.ops.dlt_forward(pts1, h4p).cpu().double().numpy()
+    Href = O.solve_dlt(pts1.cpu().double(), h4p.cpu().double()).numpy()      # same fp32-rounded inputs, fp64 solve
+    scale = np.abs(Href).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(H - Href) / scale).max() < 2e-4
+    assert (np.abs(H[:16] - g["H_cv2"]) / scale[:16]).max() < 2e-4           # integer-valued half == cv2 golden
+    assert np.all(H[:, 2, 2] == 1.0)
+    # corners map pts1 -> pts2 to well under a pixel hundredth
+    p = np.concatenate([g["pts1"].reshape(-1, 4, 2), np.ones((32, 4, 1))], 2)
+    q = np.einsum("bij,bkj->bki", H, p)
+    err = np.abs(q[..., :2] / q[..., 2:] - (pts1.cpu().double().numpy() + h4p.cpu().double().numpy()).reshape(-1, 4, 2)).max()
+    assert err < 5e-3
+
+
+def test_dlt_edge_cases(udh):
+    # B = 1, B not a multiple of the 4 warps per CTA, identity (h4p = 0), large batch
+    for B in (1, 3, 5, 1000):
+        rng = np.random.default_rng(B)
+        x0 = rng.integers(45, 148, size=B); y0 = rng.integers(45, 68, size=B)
+        pts1 = np.stack([x0, y0, x0 + 128, y0, x0 + 128, y0 + 128, x0, y0 + 128], 1).astype(np.float32)
+        h4p = rng.uniform(-45, 45, size=(B, 8)).astype(np.float32)
+        h4p[0] = 0
+        H = udh.ops.dlt_forward(torch.tensor(pts1).cuda(), torch.tensor(h4p).cuda()).cpu().double()
+        Href = O.solve_dlt(torch.tensor(pts1).double(), torch.tensor(h4p).double())
+        scale = Href.abs().amax(dim=(1, 2), keepdim=True)
+        assert ((H - Href).abs() / scale).max() < 2e-4
+        assert (H[0] - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-5
+
+
+def test_dlt_backward(udh):
+    rng = np.random.default_rng(11)
+    B = 37
+    x0 = rng.integers(45, 148, size=B); y0 = rng.integers(45, 68, size=B)
+    pts1 = torch.tensor(np.stack([x0, y0, x0 + 128, y0, x0 + 128, y0 + 128, x0, y0 + 128], 1).astype(np.float32))
+    h4p = torch.tensor(rng.uniform(-45, 45, size=(B, 8)).astype(np.float32))
+    dH = torch.tensor(rng.normal(size=(B, 3, 3)).astype(np.float32))
+    h64 = h4p.double().requires_grad_(True)
+    H64 = O.solve_dlt(pts1.double(), h64)
+    (H64 * dH.double()).sum().backward()
+    Hc = udh.ops.dlt_forward(pts1.cuda(), h4p.cuda())
+    got = udh.ops.dlt_backward(pts1.cuda(), h4p.cuda(), Hc, dH.cuda().contiguous()).cpu().double()
+    assert rel_l2(got, h64.grad) < 2e-3
+    # through the autograd.Function
+    hc = h4p.cuda().requires_grad_(True)
+    (udh.ops.solve_dlt(pts1.cuda(), hc) * dH.cuda()).sum().backward()
+    assert rel_l2(hc.grad.cpu(), h64.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ warp + losses
+def _check_pred(pred, ref, frac=0.999, tol=2e-4, mean_tol=2e-5):
+    d = np.abs(np.asarray(pred, dtype=np.float64) - np.asarray(ref, dtype=np.float64))
+    assert (d <= tol).mean() >= frac, "only %.5f of pixels within %g (max %g)" % ((d <= tol).mean(), tol, d.max())
+    assert d.mean() <= mean_tol, d.mean()
+
+
+def test_warp_window_vs_reference_numpy_twin(udh, golden_dir):
+    g = np.load(os.path.join(golden_dir, "warp_golden.npz"))
+    batch = O.make_batch(int(g["full_seed"]), 2)
+    b = dev(batch)
+    H = batch["H_gt"].float().cuda().contiguous()
+    pred, sums = udh.ops.warp_loss_forward(b["I_aug"], H, b["I2_aug"], b["patch_indices"], 128, 128)
+    _check_pred(pred.cpu().numpy()[..., 0], g["full_window"])
+
+
+def test_transformer_operator_vs_reference_numpy_twin(udh, golden_dir):
+    g = np.load(os.path.join(golden_dir, "warp_golden.npz"))
+    U = torch.tensor(g["small_img"], dtype=torch.float32).cuda()
+    theta = torch.tensor(g["small_theta"], dtype=torch.float32).cuda()
+    out, _ = udh.ops.transformer(U, theta, (24, 32))
+    ref, _ = O.transformer(U.cpu(), theta.cpu(), (24, 32))                    # fp32 oracle on the same fp32 inputs
+    d = (out.cpu() - ref).abs()
+    assert (d <= 2e-2).float().mean() > 0.995 and d.mean() < 1e-3            # 0..255 data: 2e-2 abs = 1e-4 relative
+    d64 = np.abs(out.cpu().double().numpy() - g["small_out"])
+    assert (d64 <= 5e-2).mean() > 0.99
+
+
+@pytest.mark.parametrize("seed,B", [(0, 2), (1, 2), (4, 5)])
+def test_warp_and_photometric_losses_vs_oracle(udh, seed, B):
+    batch = O.make_batch(seed, B)
+    b = dev(batch)
+    h4p = batch["gt"] + torch.tensor(np.random.default_rng(seed).normal(0, 2.0, size=(B, 8)).astype(np.float32))
+    H = O.solve_dlt(batch["pts1"], h4p)
+    ref_pred = O.transform(batch["I_aug"], H, batch["patch_indices"], 128)
+    ref = O.losses(h4p, batch["gt"], ref_pred, batch["I2_aug"])
+    Hc = H.cuda().contiguous()
+    pred, sums = udh.ops.warp_loss_forward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128)
+    _check_pred(pred.cpu().numpy(), ref_pred.numpy())
+    pl = udh.ops.photo_losses(pred, b["I2_aug"], sums, 128, 128, B).cpu().numpy()
+    L = udh.lib
+    for name, slot in (("rec_loss", L.L_REC), ("ssim_loss", L.L_SSIM), ("l1_loss", L.L_L1), ("l1_smooth_loss", L.L_L1_SMOOTH),
+                       ("ncc_loss", L.L_NCC)):
+        assert abs(pl[slot] - ref[name].item()) <= 1e-4 * abs(ref[name].item()) + 1e-6, (name, pl[slot], ref[name].item())
+
+
+def test_warp_gray_input_and_full_grid(udh):
+    """C = 1 path and config 4 (window = whole 240x320 grid, patch_indices = None)."""
+    batch = O.make_batch(9, 2, window=(320, 240, 0, 0))
+    gray = batch["I_aug"].mean(dim=3, keepdim=True).contiguous()
+    H = batch["H_gt"].float()
+    ref_pred = O.transform(gray, H, batch["patch_indices"], 240, 320)
+    ref_l1 = (ref_pred - batch["I2_aug"]).abs().mean().item()
+    pred, sums = udh.ops.warp_loss_forward(gray.cuda(), H.cuda().contiguous(), batch["I2_aug"].cuda().contiguous(), None, 320, 240)
+    _check_pred(pred.cpu().numpy(), ref_pred.numpy())
+    l1 = sums[0].item() / (2 * 240 * 320)
+    assert abs(l1 - ref_l1) <= 1e-4 * ref_l1
+
+
+@pytest.mark.parametrize("loss_name", ["l1_loss", "rec_loss", "l1_smooth_loss"])
+def test_warp_loss_backward_vs_fp64_autograd(udh, loss_name):
+    B = 3
+    batch = O.make_batch(21, B, dtype=torch.float64)
+    h4p = batch["gt"] + torch.tensor(np.random.default_rng(3).normal(0, 1.5, size=(B, 8)))
+    H = O.solve_dlt(batch["pts1"], h4p).detach().requires_grad_(True)
+    pred = O.transform(batch["I_aug"], H, batch["patch_indices"], 128)
+    O.losses(h4p, None, pred, batch["I2_aug"])[loss_name].backward()
+    lt = {"l1_loss": udh.lib.LOSS_L1, "rec_loss": udh.lib.LOSS_REC, "l1_smooth_loss": udh.lib.LOSS_L1_SMOOTH}[loss_name]
+    b = dev({k: (v.float() if isinstance(v, torch.Tensor) and v.dtype == torch.float64 else v) for k, v in batch.items()})
+    Hc = H.detach().float().cuda().contiguous()
+    _, sums = udh.ops.warp_loss_forward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, want_pred=False)
+    dH = udh.ops.warp_loss_backward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, lt, sums).cpu().double()
+    g = H.grad.clone(); g[:, 2, 2] = 0; dH[:, 2, 2] = 0                     # h33 is a constant downstream
+    for i in range(B):
+        assert rel_l2(dH[i], g[i]) < 5e-3, (i, dH[i], g[i])
+    # and the chain down to h4p
+    dh = udh.ops.dlt_backward(b["pts1"], h4p.float().cuda().contiguous(), Hc, dH.float().cuda().contiguous()).cpu().double()
+    h2 = h4p.clone().requires_grad_(True)
+    pred2 = O.transform(batch["I_aug"], O.solve_dlt(batch["pts1"], h2), batch["patch_indices"], 128)
+    O.losses(h2, None, pred2, batch["I2_aug"])[loss_name].backward()
+    assert rel_l2(dh, h2.grad) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ regressor
+def _engine(udh, B, seed, **kw):
+    return udh.engine.HomographyEngine(B, seed=seed, **kw)
+
+
+def _oracle_params(udh, seed, dtype=torch.float32):
+    flat = torch.tensor(udh.params.init_flat(seed)).to(dtype)
+    return flat, udh.params.unflatten(flat, udh.params.param_specs())
+
+
+@pytest.mark.parametrize("seed,B", [(0, 2), (1, 3)])
+def test_cnn_forward_fp32_vs_oracle(udh, seed, B):
+    eng = _engine(udh, B, seed)
+    batch = O.make_batch(seed, B)
+    out = eng.forward(dev(batch), train=False)
+    flat, params = _oracle_params(udh, seed)
+    x = torch.cat([batch["I1_aug"], batch["I2_aug"]], dim=3)
+    ref, acts = O.vgg_forward(params, x, None, return_acts=True)
+    names = list(acts.keys())   # conv1_1, conv1_2, pool1, conv2_1, conv2_2, pool2, ...
+    order = {0: "model/conv_block1/conv1", 1: "model/conv_block1/conv2", 8: "pool1", 2: "model/conv_block2/conv1",
+             3: "model/conv_block2/conv2", 9: "pool2", 4: "model/conv_block3/conv1", 5: "model/conv_block3/conv2", 10: "pool3",
+             6: "model/conv_block4/conv1", 7: "model/conv_block4/conv2"}
+    for layer, name in order.items():
+        a = acts[name].permute(0, 2, 3, 1).contiguous().numpy()              # oracle conv acts are NCHW
+        got = eng.activation(layer).cpu().numpy().reshape(a.shape)
+        assert np.abs(got - a).max() <= 2e-4 * max(1.0, np.abs(a).max()), (name, np.abs(got - a).max())
+    assert np.abs(eng.activation(11).cpu().numpy().reshape(B, 1024) - acts["fc1"].numpy()).max() < 2e-4
+    assert np.abs(out["pred_h4p"].cpu().numpy() - ref.numpy()).max() < 2e-4
+
+
+def test_e2e_golden_and_mean_corner_error(udh, golden_dir):
+    g = np.load(os.path.join(golden_dir, "e2e_golden.npz"))
+    for seed in (0, 1):
+        eng = _engine(udh, 2, seed)
+        batch = O.make_batch(seed, 2)
+        out = eng.forward(dev(batch), train=False)
+        d = eng.losses_dict(out)
+        assert np.abs(out["pred_h4p"].cpu().numpy() - g["s%d_pred_h4p" % seed]).max() < 5e-4
+        Hs = np.abs(g["s%d_H_mat" % seed]).max()
+        assert np.abs(out["H_mat"].cpu().numpy() - g["s%d_H_mat" % seed]).max() < 5e-4 * Hs
+        _check_pred(out["pred_I2"].cpu().numpy(), g["s%d_pred_I2" % seed], tol=1e-3, mean_tol=1e-4)
+        # mean corner error (reference definition: bounded_h_loss; also h_loss) within 1e-3 px
+        assert abs(d["bounded_h_loss"] - float(g["s%d_bounded_h_loss" % seed])) <= 1e-3
+        assert abs(d["h_loss"] - float(g["s%d_h_loss" % seed])) <= 1e-3
+        assert d["num_fail"] == float(g["s%d_num_fail" % seed])
+        for k in ("rec_loss", "ssim_loss", "l1_loss", "l1_smooth_loss", "ncc_loss"):
+            assert abs(d[k] - float(g["s%d_%s" % (seed, k)])) <= 2e-4 * abs(float(g["s%d_%s" % (seed, k)])) + 1e-6, k
+        per = out["batch_h_loss"].cpu().numpy()
+        assert np.abs(per - g["s%d_batch_h_loss" % seed]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("loss_type,lr", [("h_loss", 5e-4), ("l1_loss", 1e-4)])
+def test_train_step_gradients_and_adam_vs_oracle(udh, loss_type, lr):
+    seed, B = 0, 2
+    specs = udh.params.param_specs()
+    eng = _engine(udh, B, seed, loss_type=loss_type, lr=lr)
+    batch = O.make_batch(seed, B)
+    db = dev(batch)
+    # train-mode forward draws the dropout masks on the device; the oracle reuses exactly those masks
+    out = eng.forward(db, train=True)
+    m1, m2 = eng.dropout_masks()
+    keep = (m1.cpu().float(), m2.cpu().float())
+    assert 0.45 < keep[0].mean() < 0.55 and 0.4 < keep[1].mean() < 0.6
+    eng.backward(db, out)
+    flat, _ = _oracle_params(udh, seed)
+    newp, m, v, ref_out, g = O.train_step(flat, torch.zeros_like(flat), torch.zeros_like(flat), 0, batch, specs,
+                                          loss_type=loss_type, lr=lr, keep_masks=keep)
+    assert np.abs(out["pred_h4p"].cpu().numpy() - ref_out["pred_h4p"].numpy()).max() < 5e-4
+    got = eng.grads.cpu()
+    for name, s in specs.items():
+        a, r = got[s.offset:s.offset + s.size], g[s.offset:s.offset + s.size]
+        assert rel_l2(a, r) < 2e-3, (name, rel_l2(a, r))
+    eng.update()
+    # TF-Adam's first step moves every touched weight by ~lr * sign(g): compare where the gradient is not ~0
+    upd, ref_upd = (eng.params.cpu() - flat), (newp - flat)
+    big = g.abs() > 1e-3 * g.abs().max()
+    assert (upd[big] - ref_upd[big]).abs().max() <= 0.02 * lr
+    assert eng.grads.abs().max().item() == 0.0                                # zero_grad fused into the update
+    assert eng.global_step == 1
+
+
+def test_adam_kernel_vs_oracle(udh):
+    n = 4096 + 32
+    rng = np.random.default_rng(0)
+    p = torch.tensor(rng.normal(size=n).astype(np.float32)); g = torch.tensor(rng.normal(size=n).astype(np.float32))
+    m = torch.tensor(rng.normal(size=n).astype(np.float32) * 0.1); v = torch.tensor(rng.uniform(0, 1, size=n).astype(np.float32))
+    import math
+    t, lr = 7, 3e-4
+    alpha = lr * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t)
+    rp, rm, rv = O.adam_step(p.double(), g.double() * 0.5, m.double(), v.double(), t, lr)
+    pc, gc, mc, vc = p.cuda(), g.cuda(), m.cuda(), v.cuda()
+    udh.ops.adam_step(pc, gc, mc, vc, alpha, grad_scale=0.5, zero_grad=False)
+    assert (pc.cpu().double() - rp).abs().max() < 1e-6 and (mc.cpu().double() - rm).abs().max() < 1e-6
+    assert (vc.cpu().double() - rv).abs().max() < 1e-6 and torch.equal(gc.cpu(), g)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_B128(udh):
+    """BASELINE config sizes (B = 128): properties that need no full-size oracle run."""
+    B = 128
+    batch = O.make_batch(100, 4)
+    rep = lambda t: t.repeat(B // 4, *([1] * (t.dim() - 1))).cuda().contiguous()
+    db = {k: rep(v) for k, v in batch.items() if isinstance(v, torch.Tensor) and k != "H_gt"}
+    eng = _engine(udh, B, 0)
+    out = eng.forward(db, train=False)
+    h = out["pred_h4p"]
+    # (1) batch invariance: replicated samples give identical predictions, and equal the B = 4 run
+    assert torch.equal(h[:4], h[4:8]) and torch.equal(h[:4], h[-4:])
+    eng4 = _engine(udh, 4, 0)
+    out4 = eng4.forward(dev(batch), train=False)
+    assert (out4["pred_h4p"] - h[:4]).abs().max().item() < 1e-5
+    # (2) warp with the ground-truth homography reproduces I2 up to the uint8 cast of I'
+    Hgt = udh.ops.dlt_forward(db["pts1"], db["gt"])
+    pred, sums = udh.ops.warp_loss_forward(db["I_aug"], Hgt, db["I2_aug"], db["patch_indices"], 128, 128)
+    assert sums[0].item() / (B * 128 * 128) < 1.0 / 69.0
+    # (3) means are replication invariant
+    d4, d128 = eng4.losses_dict(out4), eng.losses_dict(out)
+    for k in ("l1_loss", "rec_loss", "ssim_loss", "l1_smooth_loss", "h_loss", "bounded_h_loss"):
+        assert abs(d4[k] - d128[k]) <= 1e-5 * max(1.0, abs(d4[k])), k
+    assert d128["num_fail"] == d4["num_fail"] * (B // 4)

@@ -1,0 +1,73 @@
+"""ctypes binding of libudh.so (include/udh.h).  No CPU fallback: if the library is missing it is built with nvcc,
+and if that is impossible the import fails loudly."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+from . import build_ext
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libudh.so")
+
+OK, EINVAL, ECUDA, ENOSUP, EWS = 0, -1, -2, -3, -4
+NUMERIC_FP32, NUMERIC_BF16 = 0, 1
+LOSS_L1, LOSS_REC, LOSS_L1_SMOOTH = 0, 1, 2
+NSUMS, NLOSSES, NMETRICS = 8, 8, 4
+L_REC, L_SSIM, L_L1, L_L1_SMOOTH, L_NCC = 0, 1, 2, 3, 4
+M_H_LOSS, M_BOUNDED_H_LOSS, M_NUM_FAIL, M_ACE = 0, 1, 2, 3
+
+# name -> (restype, argtypes); every symbol include/udh.h declares
+SIGNATURES = {
+    "udh_version": (c_int, []),
+    "udh_last_error": (c_char_p, []),
+    "udh_device_available": (c_int, []),
+    "udh_dlt_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_dlt_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_warp_loss_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_warp_loss_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                  c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_ssim_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "udh_photo_losses_finalize": (c_int, [c_void_p, c_double, c_double, c_void_p, c_void_p]),
+    "udh_transformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "udh_h4p_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "udh_cnn_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "udh_cnn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_uint64, c_int,
+                            c_void_p]),
+    "udh_cnn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
+                            c_void_p]),
+    "udh_cnn_dropout_masks": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p)]),
+    "udh_cnn_activation": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_size_t)]),
+    "udh_param_offset": (c_int, [c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "udh_param_total_floats": (c_size_t, [c_int]),
+    "udh_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
+                              c_int, c_void_p]),
+}
+
+
+class UdhError(RuntimeError):
+    pass
+
+
+def _load():
+    if build_ext.needs_build():
+        build_ext.build()      # raises if nvcc is unavailable: there is deliberately no pure-Python/CPU path
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != OK:
+        raise UdhError("%s failed (%d): %s" % (what or "libudh call", rc, lib.udh_last_error().decode()))
+
+
+def require_device():
+    if not lib.udh_device_available():
+        raise UdhError("no CUDA device: libudh has no CPU fallback (the CPU oracle lives in oracle/ and is test-only)")

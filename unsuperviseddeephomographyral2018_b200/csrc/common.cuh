@@ -1,0 +1,73 @@
+// Shared helpers of libudh (error reporting, launch checks, warp/block reductions).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/udh.h"
+
+namespace udh {
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return UDH_ECUDA;
+  }
+  return UDH_OK;
+}
+
+#define UDH_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      udh::set_error(__VA_ARGS__);    \
+      return UDH_EINVAL;              \
+    }                                 \
+  } while (0)
+
+#define UDH_CUDA(call)                                                      \
+  do {                                                                      \
+    cudaError_t e__ = (call);                                               \
+    if (e__ != cudaSuccess) {                                               \
+      udh::set_error("%s failed: %s", #call, cudaGetErrorString(e__));      \
+      return UDH_ECUDA;                                                     \
+    }                                                                       \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  `scratch` holds NV * 32 elements of T.
+template <typename T, int NV>
+__device__ __forceinline__ void block_sum(T (&v)[NV], T* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) scratch[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      T x = lane < nwarp ? scratch[i * 32 + lane] : T(0);
+      v[i] = warp_sum(x);
+    }
+  }
+}
+
+}  // namespace udh

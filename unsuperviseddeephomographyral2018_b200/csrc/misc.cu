@@ -1,0 +1,105 @@
+// Small entry points: error reporting, h4p losses / test metrics (Row L), TF-1 Adam (Row O).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace udh {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// h_loss = sqrt(mean_{B x 8}(pred-gt)^2) (homography_model.py:288); test metrics (:274-281):
+// batch_h_loss_b = sqrt(mean_8 (pred-gt)^2), identity_b = sqrt(mean_8 gt^2), failure = batch >= identity,
+// bounded = mean_b(failure ? identity : batch).  One CTA; B is small (<= a few thousand).
+__global__ void __launch_bounds__(256) h4p_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int B,
+                                                       float* __restrict__ metrics, float* __restrict__ per_sample,
+                                                       float* __restrict__ dpred) {
+  __shared__ double red[4 * 32];
+  __shared__ float s_hloss;
+  double acc[4] = {0, 0, 0, 0};   // sum sq, sum bounded, num fail, sum corner distance
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float sq = 0.f, id = 0.f, dist = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float dx = pred[b * 8 + 2 * i] - gt[b * 8 + 2 * i], dy = pred[b * 8 + 2 * i + 1] - gt[b * 8 + 2 * i + 1];
+      sq += dx * dx + dy * dy;
+      id += gt[b * 8 + 2 * i] * gt[b * 8 + 2 * i] + gt[b * 8 + 2 * i + 1] * gt[b * 8 + 2 * i + 1];
+      dist += sqrtf(dx * dx + dy * dy);
+    }
+    const float bh = sqrtf(sq / 8.0f), ih = sqrtf(id / 8.0f);
+    const bool fail = bh >= ih;
+    if (per_sample) per_sample[b] = bh;
+    acc[0] += sq; acc[1] += fail ? ih : bh; acc[2] += fail ? 1.0 : 0.0; acc[3] += dist * 0.25f;
+  }
+  block_sum<double, 4>(acc, red);
+  if (threadIdx.x == 0) {
+    const float hl = (float)sqrt(acc[0] / (8.0 * B));
+    metrics[UDH_M_H_LOSS] = hl;
+    metrics[UDH_M_BOUNDED_H_LOSS] = (float)(acc[1] / B);
+    metrics[UDH_M_NUM_FAIL] = (float)acc[2];
+    metrics[UDH_M_ACE] = (float)(acc[3] / B);
+    s_hloss = hl;
+  }
+  __syncthreads();
+  if (dpred) {
+    // d sqrt(mean d^2) / d pred = d / (N * h_loss)
+    const float k = s_hloss > 0.f ? 1.0f / (8.0f * (float)B * s_hloss) : 0.f;
+    for (int i = threadIdx.x; i < B * 8; i += blockDim.x) dpred[i] = (pred[i] - gt[i]) * k;
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
+                                                   float4* __restrict__ v, size_t n4, float alpha, float b1, float b2,
+                                                   float eps, float gs, int zero_grad) {
+  const float c1 = 1.0f - b1, c2 = 1.0f - b2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
+    gv.x *= gs; gv.y *= gs; gv.z *= gs; gv.w *= gs;
+    mv.x = b1 * mv.x + c1 * gv.x; mv.y = b1 * mv.y + c1 * gv.y; mv.z = b1 * mv.z + c1 * gv.z; mv.w = b1 * mv.w + c1 * gv.w;
+    vv.x = b2 * vv.x + c2 * gv.x * gv.x; vv.y = b2 * vv.y + c2 * gv.y * gv.y;
+    vv.z = b2 * vv.z + c2 * gv.z * gv.z; vv.w = b2 * vv.w + c2 * gv.w * gv.w;
+    pv.x -= alpha * mv.x / (sqrtf(vv.x) + eps); pv.y -= alpha * mv.y / (sqrtf(vv.y) + eps);
+    pv.z -= alpha * mv.z / (sqrtf(vv.z) + eps); pv.w -= alpha * mv.w / (sqrtf(vv.w) + eps);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+}  // namespace udh
+
+extern "C" int udh_version(void) { return 100; }
+
+extern "C" const char* udh_last_error(void) { return udh::g_err; }
+
+extern "C" int udh_device_available(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n > 0 ? 1 : 0;
+}
+
+extern "C" int udh_h4p_loss(const float* pred, const float* gt, int B, float* metrics, float* per_sample, float* dpred,
+                            void* stream) {
+  UDH_REQUIRE(pred && gt && metrics && B >= 1, "udh_h4p_loss: bad arguments");
+  udh::h4p_loss_kernel<<<1, 256, 0, udh::as_stream(stream)>>>(pred, gt, B, metrics, per_sample, dpred);
+  return udh::check_launch("udh_h4p_loss");
+}
+
+extern "C" int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                             float eps, float grad_scale, int zero_grad, void* stream) {
+  UDH_REQUIRE(p && g && m && v, "udh_adam_step: null pointer");
+  UDH_REQUIRE(n % 4 == 0, "udh_adam_step: n must be a multiple of 4 (flat buffers are padded to 32 floats)");
+  UDH_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "udh_adam_step: buffers must be 16-byte aligned");
+  if (n == 0) return UDH_OK;
+  const size_t n4 = n / 4;
+  const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  udh::adam_kernel<<<blocks, 256, 0, udh::as_stream(stream)>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
+                                                              beta1, beta2, eps, grad_scale, zero_grad);
+  return udh::check_launch("udh_adam_step");
+}

@@ -1,0 +1,181 @@
+"""Training / evaluation engine of the unsupervised-homography path on one GPU (one process per GPU).
+
+Owns the flat fp32 parameter / gradient / Adam buffers and the activation workspace, and strings the libudh calls
+into the reference's step (code/homography_CNN_synthetic.py:229-278,333-353):
+    regressor fwd -> h4p losses -> DLT -> fused warp + photometric reductions -> backward of the selected loss
+    -> gradient mean over ranks (one NCCL allreduce of the flat buffer) -> TF-1 Adam with staircase decay.
+All arithmetic is in libudh's CUDA kernels; torch provides memory, streams and torch.distributed.
+"""
+import ctypes
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib, ops, params as P
+from ._lib import check, lib
+
+LOSS_TYPES = ("h_loss", "rec_loss", "ssim_loss", "l1_loss", "l1_smooth_loss", "ncc_loss")
+_PHOTO_BWD = {"l1_loss": _lib.LOSS_L1, "rec_loss": _lib.LOSS_REC, "l1_smooth_loss": _lib.LOSS_L1_SMOOTH}
+NUMERIC = {"fp32": _lib.NUMERIC_FP32, "bf16": _lib.NUMERIC_BF16}
+
+
+def decay_steps(lr, min_lr, num_total_steps=150000, decay_rate=0.96):
+    """homography_CNN_synthetic.py:161-169."""
+    return int((math.log(decay_rate) * num_total_steps) / math.log(min_lr * 1.0 / lr))
+
+
+def learning_rate(step, lr, min_lr, num_total_steps=150000, decay_rate=0.96):
+    """tf.train.exponential_decay(lr, step, decay_steps, 0.96, staircase=True)."""
+    return lr * decay_rate ** (step // decay_steps(lr, min_lr, num_total_steps, decay_rate))
+
+
+class HomographyEngine(object):
+    def __init__(self, batch_size, patch_size=128, img_h=240, img_w=320, numeric="fp32", seed=0, device=None,
+                 lr=1e-4, min_lr=0.9e-4, loss_type="l1_loss", process_group=None, world_size=1):
+        _lib.require_device()
+        if loss_type not in LOSS_TYPES:
+            raise ValueError("unknown loss_type %r" % (loss_type,))
+        self.device = torch.device(device if device is not None else "cuda")
+        self.B, self.Pz, self.img_h, self.img_w = int(batch_size), int(patch_size), int(img_h), int(img_w)
+        self.numeric = NUMERIC[numeric]
+        self.numeric_name = numeric
+        self.loss_type = loss_type
+        self.lr, self.min_lr = lr, min_lr
+        self.specs = P.param_specs(patch_size)
+        n = P.total_floats(self.specs)
+        assert n == lib.udh_param_total_floats(patch_size), "python / C parameter layouts disagree"
+        self.params = torch.zeros(n, device=self.device, dtype=torch.float32)
+        self.grads = torch.zeros_like(self.params)
+        self.adam_m = torch.zeros_like(self.params)
+        self.adam_v = torch.zeros_like(self.params)
+        if seed is not None:
+            self.load_flat(P.init_flat(seed, patch_size))
+        self.ws_bytes = lib.udh_cnn_workspace_bytes(self.B, self.Pz, self.numeric)
+        if self.ws_bytes == 0:
+            raise _lib.UdhError("unsupported batch / patch size (%d, %d)" % (self.B, self.Pz))
+        self.ws = torch.empty(self.ws_bytes, device=self.device, dtype=torch.uint8)
+        self.global_step = 0
+        self.pg = process_group
+        self.world_size = world_size
+        self.dropout_seed = 0x5EED0000 + (seed or 0)
+        self.kernel_launches = 0   # kernels launched by the last forward/backward/update (counted, see _count)
+
+    # ------------------------------------------------------------------ parameters
+    def load_flat(self, flat_np):
+        self.params.copy_(torch.as_tensor(flat_np, dtype=torch.float32))
+
+    def named_parameters(self):
+        return P.unflatten(self.params, self.specs)
+
+    def named_gradients(self):
+        return P.unflatten(self.grads, self.specs)
+
+    def state_dict(self):
+        return OrderedDict(params=self.params.cpu(), adam_m=self.adam_m.cpu(), adam_v=self.adam_v.cpu(),
+                           global_step=self.global_step, patch_size=self.Pz)
+
+    def load_state_dict(self, sd, reset_step=False):
+        self.params.copy_(sd["params"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"])
+        self.global_step = 0 if reset_step else int(sd["global_step"])
+
+    # ------------------------------------------------------------------ forward
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def forward(self, batch, train=False, want_pred=True, dropout_seed=None):
+        """batch: dict of CUDA tensors — I1_aug, I2_aug [B,P,P,1]; I_aug [B,Hh,W,C]; pts1 [B,8]; gt [B,8] or None;
+        patch_indices [B,P*P] int32.  Returns dict with the reference model's result attributes
+        (pred_h4p, H_mat, pred_I2, the six losses; test metrics when gt is given)."""
+        B, Pz = self.B, self.Pz
+        I1, I2 = batch["I1_aug"], batch["I2_aug"]
+        assert I1.shape[0] == B and I1.shape[1] == Pz, "batch shape does not match the engine"
+        st = ops._stream()
+        out = OrderedDict()
+        h4p = torch.empty(B, 8, device=self.device, dtype=torch.float32)
+        seed = self.dropout_seed + self.global_step if dropout_seed is None else dropout_seed
+        check(lib.udh_cnn_fwd(self._p(self.params), self._p(I1), self._p(I2), self._p(h4p), self._p(self.ws), self.ws_bytes,
+                              B, Pz, int(train), seed, self.numeric, st), "udh_cnn_fwd")
+        out["pred_h4p"] = h4p
+        gt = batch.get("gt")
+        if gt is not None:
+            metrics, per, dpred = ops.h4p_loss(h4p, gt, want_grad=train and self.loss_type == "h_loss", want_per_sample=not train)
+            out["h4p_metrics"], out["batch_h_loss"], out["_dpred"] = metrics, per, dpred
+        H = ops.dlt_forward(batch["pts1"], h4p)
+        out["H_mat"] = H
+        pred, sums = ops.warp_loss_forward(batch["I_aug"], H, I2, batch.get("patch_indices"), Pz, Pz, want_pred=True)
+        out["pred_I2"] = pred
+        out["_sums"] = sums
+        out["photo_losses"] = ops.photo_losses(pred, I2, sums, Pz, Pz, B)
+        return out
+
+    @staticmethod
+    def losses_dict(out):
+        """Host-side view (one D2H sync) named like the reference's attributes."""
+        pl = out["photo_losses"].tolist()
+        d = OrderedDict(rec_loss=pl[_lib.L_REC], ssim_loss=pl[_lib.L_SSIM], l1_loss=pl[_lib.L_L1],
+                        l1_smooth_loss=pl[_lib.L_L1_SMOOTH], ncc_loss=pl[_lib.L_NCC])
+        if "h4p_metrics" in out:
+            m = out["h4p_metrics"].tolist()
+            d.update(h_loss=m[_lib.M_H_LOSS], bounded_h_loss=m[_lib.M_BOUNDED_H_LOSS], num_fail=m[_lib.M_NUM_FAIL],
+                     ace=m[_lib.M_ACE])
+        return d
+
+    # ------------------------------------------------------------------ backward + update
+    def backward(self, batch, out):
+        """Gradient of the selected loss into self.grads (which must be zero on entry)."""
+        lt = self.loss_type
+        if lt == "h_loss":
+            dpred = out["_dpred"]
+            if dpred is None:
+                raise _lib.UdhError("h_loss needs gt")
+        elif lt in _PHOTO_BWD:
+            dH = ops.warp_loss_backward(batch["I_aug"], out["H_mat"], batch["I2_aug"], batch.get("patch_indices"), self.Pz,
+                                        self.Pz, _PHOTO_BWD[lt], out["_sums"], 1.0)
+            dpred = ops.dlt_backward(batch["pts1"], out["pred_h4p"], out["H_mat"], dH)
+        else:
+            raise _lib.UdhError("loss_type %s has no CUDA backward yet (SURVEY §8f item 3)" % lt)
+        out["_dh4p"] = dpred
+        check(lib.udh_cnn_bwd(self._p(self.params), self._p(batch["I1_aug"]), self._p(batch["I2_aug"]), self._p(dpred),
+                              self._p(self.grads), self._p(self.ws), self.ws_bytes, self.B, self.Pz, 1, self.numeric,
+                              ops._stream()), "udh_cnn_bwd")
+
+    def allreduce_grads(self):
+        """Row G: utils/utils.py:380-403 get_average_grads == allreduce(sum) here, 1/N folded into Adam."""
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+
+    def update(self):
+        t = self.global_step + 1
+        lr_t = learning_rate(self.global_step, self.lr, self.min_lr)
+        alpha = lr_t * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, alpha, 0.9, 0.999, 1e-8,
+                      1.0 / self.world_size, zero_grad=True)
+        self.global_step += 1
+        return lr_t
+
+    def train_step(self, batch):
+        out = self.forward(batch, train=True)
+        self.backward(batch, out)
+        self.allreduce_grads()
+        out["lr"] = self.update()
+        return out
+
+    # ------------------------------------------------------------------ test helpers
+    def dropout_masks(self):
+        m1, m2 = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib.udh_cnn_dropout_masks(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, ctypes.byref(m1),
+                                        ctypes.byref(m2)), "udh_cnn_dropout_masks")
+        base = self.ws.data_ptr()
+        s = self.Pz // 8
+        n1, n2 = self.B * s * s * 128, self.B * 1024
+        a = self.ws[m1.value - base: m1.value - base + n1].reshape(self.B, s, s, 128)
+        b = self.ws[m2.value - base: m2.value - base + n2].reshape(self.B, 1024)
+        return a, b
+
+    def activation(self, layer):
+        ptr, numel = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib.udh_cnn_activation(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, layer, ctypes.byref(ptr),
+                                     ctypes.byref(numel)), "udh_cnn_activation")
+        off = ptr.value - self.ws.data_ptr()
+        return self.ws[off: off + numel.value * 4].view(torch.float32)
