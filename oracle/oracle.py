@@ -84,8 +84,10 @@ def meshgrid(height, width, dtype):
     return torch.stack([x_t.reshape(-1), y_t.reshape(-1), torch.ones(height * width, dtype=dtype)], dim=0)
 
 
-def interpolate(im, x, y):
-    """tf_spatial_transformer.py:76-139.  im [B,H,W,C]; x, y flat [B*H_out*W_out] in [-1,1] units."""
+def interpolate(im, x, y, return_cond=False):
+    """tf_spatial_transformer.py:76-139.  im [B,H,W,C]; x, y flat [B*H_out*W_out] in [-1,1] units.
+    return_cond: also return sum_k |w_k I_k| — the magnitude that cancels for out-of-range samples; fp32 results are
+    only defined up to ~eps * that (tests scale their tolerance with it)."""
     B, H, W, C = im.shape
     dt = im.dtype
     n_per = x.numel() // B
@@ -110,10 +112,13 @@ def interpolate(im, x, y):
     wb = ((x1f - x) * (y - y0f)).unsqueeze(1)
     wc = ((x - x0f) * (y1f - y)).unsqueeze(1)
     wd = ((x - x0f) * (y - y0f)).unsqueeze(1)
-    return ((wa * Ia + wb * Ib) + wc * Ic) + wd * Id                 # :138 add_n
+    out = ((wa * Ia + wb * Ib) + wc * Ic) + wd * Id                  # :138 add_n
+    if return_cond:
+        return out, (wa * Ia).abs() + (wb * Ib).abs() + (wc * Ic).abs() + (wd * Id).abs()
+    return out
 
 
-def transformer(U, theta, out_size):
+def transformer(U, theta, out_size, return_cond=False):
     """tf_spatial_transformer.py:182-251.  U [B,H,W,C], theta [B,3,3] (normalised H'), out_size (H_out,W_out).
     Returns (output [B,H_out,W_out,C], condition)."""
     B, H, W, C = U.shape
@@ -126,6 +131,9 @@ def transformer(U, theta, out_size):
     smallers = 1e-6 * (1.0 - (t_s.abs() >= small).to(dt))           # :230-231
     t_s = t_s + smallers                                             # :234
     condition = (t_s.abs() > small).to(dt).sum()                     # :235
+    if return_cond:
+        out, cond = interpolate(U, x_s / t_s, y_s / t_s, True)
+        return out.reshape(B, oh, ow, C), cond.reshape(B, oh, ow, C)
     out = interpolate(U, x_s / t_s, y_s / t_s)                       # :239-242
     return out.reshape(B, oh, ow, C), condition
 
@@ -137,15 +145,19 @@ def norm_matrices(img_w, img_h, dtype):
     return torch.tensor(M, dtype=dtype), torch.tensor(M_inv.astype(np.float32), dtype=dtype)
 
 
-def transform(I, H_mat, patch_indices, patch_size, patch_w=None):
+def transform(I, H_mat, patch_indices, patch_size, patch_w=None, return_cond=False):
     """homography_model.py:252-269: H' = M^-1 H M, full-grid warp of I [B,Hh,W,C], channel mean,
     flat gather of `patch_indices` [B,P*P] (+ b*Hh*W, :74-76) -> pred_I2 [B,P,P,1]."""
     B, Hh, W, C = I.shape
     M, M_inv = norm_matrices(W, Hh, I.dtype)
     Hn = torch.matmul(torch.matmul(M_inv.expand(B, 3, 3), H_mat), M.expand(B, 3, 3))     # :254
+    idx = patch_indices.reshape(B, -1).to(torch.int64) + (torch.arange(B, dtype=torch.int64) * (Hh * W)).unsqueeze(1)
+    if return_cond:
+        warped, cond = transformer(I, Hn, (Hh, W), True)
+        shape = (B, patch_size, patch_w or patch_size, 1)
+        return warped.mean(dim=3).reshape(-1)[idx.reshape(-1)].reshape(shape), cond.mean(dim=3).reshape(-1)[idx.reshape(-1)].reshape(shape)
     warped, _ = transformer(I, Hn, (Hh, W))                                              # :257
     gray = warped.mean(dim=3).reshape(-1)                                                # :263-264
-    idx = patch_indices.reshape(B, -1).to(torch.int64) + (torch.arange(B, dtype=torch.int64) * (Hh * W)).unsqueeze(1)
     return gray[idx.reshape(-1)].reshape(B, patch_size, patch_w or patch_size, 1)       # :267-269
 
 

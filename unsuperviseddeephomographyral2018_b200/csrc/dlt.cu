@@ -2,20 +2,23 @@
 // (lane r < 8 owns row r), LU with partial pivoting and back substitution run on warp shuffles.
 // Reference: code/homography_model.py:169-250 (assembly with Aux_M*, utils/utils.py:11-122; tf.matrix_solve).
 // Latency-bound (~100 B, ~1 kFLOP per sample): no tensor cores, no shared memory traffic.
+// I/O is fp32 like the reference; the elimination itself runs in fp64 registers: cond(A) ~ 5e5 in pixel units, so
+// an fp32 LU carries ~1e-4 relative noise that depends on the LU variant (LAPACK vs cuSOLVER vs this one) — there
+// is no canonical fp32 answer to match, and fp64 costs nothing in a latency-bound kernel.
 #include "common.cuh"
 
 namespace udh {
 
 // Solve the 8x8 system whose row `lane` (< 8) is a[0..7] | a[8].  All 32 lanes call; on return every lane holds
 // the full solution x[0..7].  Partial pivoting picks the first row of maximal |a[k]| (LAPACK isamax rule).
-__device__ __forceinline__ void lu_solve_warp(float (&a)[9], float (&x)[8], int lane) {
+__device__ __forceinline__ void lu_solve_warp(double (&a)[9], double (&x)[8], int lane) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float best = (lane >= k && lane < 8) ? fabsf(a[k]) : -1.0f;
+    double best = (lane >= k && lane < 8) ? fabs(a[k]) : -1.0;
     int idx = lane;
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      double ob = __shfl_xor_sync(0xffffffffu, best, o);
       int oi = __shfl_xor_sync(0xffffffffu, idx, o);
       if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
     }
@@ -23,34 +26,34 @@ __device__ __forceinline__ void lu_solve_warp(float (&a)[9], float (&x)[8], int 
     const int src = (lane == k) ? piv : ((lane == piv) ? k : lane);
 #pragma unroll
     for (int c = k; c < 9; ++c) a[c] = __shfl_sync(0xffffffffu, a[c], src);   // row swap k <-> piv
-    float pk[9];
+    double pk[9];
 #pragma unroll
     for (int c = k; c < 9; ++c) pk[c] = __shfl_sync(0xffffffffu, a[c], k);
     if (lane > k && lane < 8) {
-      const float f = a[k] / pk[k];
+      const double f = a[k] / pk[k];
 #pragma unroll
-      for (int c = k + 1; c < 9; ++c) a[c] = fmaf(-f, pk[c], a[c]);
-      a[k] = 0.0f;
+      for (int c = k + 1; c < 9; ++c) a[c] = fma(-f, pk[c], a[c]);
+      a[k] = 0.0;
     }
   }
 #pragma unroll
   for (int k = 7; k >= 0; --k) {
-    const float xk = __shfl_sync(0xffffffffu, a[8] / a[k], k);
+    const double xk = __shfl_sync(0xffffffffu, a[8] / a[k], k);
     x[k] = xk;
-    if (lane < k) a[8] = fmaf(-a[k], xk, a[8]);
+    if (lane < k) a[8] = fma(-a[k], xk, a[8]);
   }
 }
 
 // Row `r` of [A|b] (homography_model.py:223-238): corner i = r/2, (x,y) = pts1, (u,v) = pts1 + h4p
 //   even r: [0,0,0,-x,-y,-1, v*x, v*y | -v]      odd r: [x,y,1,0,0,0,-u*x,-u*y | u]
-__device__ __forceinline__ void build_row(const float* __restrict__ p1, const float* __restrict__ h, int r, float (&a)[9]) {
+__device__ __forceinline__ void build_row(const float* __restrict__ p1, const float* __restrict__ h, int r, double (&a)[9]) {
   const int i = r >> 1;
-  const float x = p1[2 * i], y = p1[2 * i + 1];
-  const float u = x + h[2 * i], v = y + h[2 * i + 1];
+  const double x = p1[2 * i], y = p1[2 * i + 1];
+  const double u = (double)(p1[2 * i] + h[2 * i]), v = (double)(p1[2 * i + 1] + h[2 * i + 1]);   // pts2 is an fp32 tensor (:176)
   if ((r & 1) == 0) {
-    a[0] = 0.f; a[1] = 0.f; a[2] = 0.f; a[3] = -x; a[4] = -y; a[5] = -1.f; a[6] = v * x; a[7] = v * y; a[8] = -v;
+    a[0] = 0.; a[1] = 0.; a[2] = 0.; a[3] = -x; a[4] = -y; a[5] = -1.; a[6] = v * x; a[7] = v * y; a[8] = -v;
   } else {
-    a[0] = x; a[1] = y; a[2] = 1.f; a[3] = 0.f; a[4] = 0.f; a[5] = 0.f; a[6] = -u * x; a[7] = -u * y; a[8] = u;
+    a[0] = x; a[1] = y; a[2] = 1.; a[3] = 0.; a[4] = 0.; a[5] = 0.; a[6] = -u * x; a[7] = -u * y; a[8] = u;
   }
 }
 
@@ -59,16 +62,16 @@ __global__ void __launch_bounds__(128) dlt_fwd_kernel(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;                                        // warp-uniform
-  float a[9], x[8];
+  double a[9], x[8];
   if (lane < 8) build_row(pts1 + (size_t)b * 8, h4p + (size_t)b * 8, lane, a);
   else {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) a[c] = 0.f;
+    for (int c = 0; c < 9; ++c) a[c] = 0.;
   }
   lu_solve_warp(a, x, lane);
   float out = 1.0f;                                          // h33 = 1 (homography_model.py:247-250)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) if (lane == k) out = x[k];
+  for (int k = 0; k < 8; ++k) if (lane == k) out = (float)x[k];
   if (lane < 9) H[(size_t)b * 9 + lane] = out;
 }
 
@@ -83,23 +86,23 @@ __global__ void __launch_bounds__(128) dlt_bwd_kernel(const float* __restrict__ 
   if (b >= B) return;
   const float* p1 = pts1 + (size_t)b * 8;
   const float* h = h4p + (size_t)b * 8;
-  float a[9], lam[8];
+  double a[9], lam[8];
 #pragma unroll
-  for (int c = 0; c < 9; ++c) a[c] = 0.f;
+  for (int c = 0; c < 9; ++c) a[c] = 0.;
   if (lane < 8) {
     // row `lane` of A^T = column `lane` of A
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float x = p1[2 * i], y = p1[2 * i + 1];
-      const float u = x + h[2 * i], v = y + h[2 * i + 1];
-      float e0, e1;                                          // entries at rows 2i, 2i+1 of column `lane`
+      const double x = p1[2 * i], y = p1[2 * i + 1];
+      const double u = (double)(p1[2 * i] + h[2 * i]), v = (double)(p1[2 * i + 1] + h[2 * i + 1]);
+      double e0, e1;                                         // entries at rows 2i, 2i+1 of column `lane`
       switch (lane) {
-        case 0: e0 = 0.f; e1 = x; break;
-        case 1: e0 = 0.f; e1 = y; break;
-        case 2: e0 = 0.f; e1 = 1.f; break;
-        case 3: e0 = -x; e1 = 0.f; break;
-        case 4: e0 = -y; e1 = 0.f; break;
-        case 5: e0 = -1.f; e1 = 0.f; break;
+        case 0: e0 = 0.; e1 = x; break;
+        case 1: e0 = 0.; e1 = y; break;
+        case 2: e0 = 0.; e1 = 1.; break;
+        case 3: e0 = -x; e1 = 0.; break;
+        case 4: e0 = -y; e1 = 0.; break;
+        case 5: e0 = -1.; e1 = 0.; break;
         case 6: e0 = v * x; e1 = -u * x; break;
         default: e0 = v * y; e1 = -u * y; break;
       }
@@ -108,13 +111,13 @@ __global__ void __launch_bounds__(128) dlt_bwd_kernel(const float* __restrict__ 
     a[8] = dH[(size_t)b * 9 + lane];
   }
   lu_solve_warp(a, lam, lane);
-  const float h6 = H[(size_t)b * 9 + 6], h7 = H[(size_t)b * 9 + 7];
+  const double h6 = H[(size_t)b * 9 + 6], h7 = H[(size_t)b * 9 + 7];
   float out = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float s = fmaf(h6, p1[2 * i], fmaf(h7, p1[2 * i + 1], 1.0f));
-    if (lane == 2 * i) out = lam[2 * i + 1] * s;             // d/du_i
-    if (lane == 2 * i + 1) out = -lam[2 * i] * s;            // d/dv_i
+    const double s = fma(h6, (double)p1[2 * i], fma(h7, (double)p1[2 * i + 1], 1.0));
+    if (lane == 2 * i) out = (float)(lam[2 * i + 1] * s);    // d/du_i
+    if (lane == 2 * i + 1) out = (float)(-lam[2 * i] * s);   // d/dv_i
   }
   if (lane < 8) dh4p[(size_t)b * 8 + lane] = out;
 }

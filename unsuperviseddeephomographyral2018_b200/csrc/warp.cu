@@ -65,12 +65,19 @@ __device__ __forceinline__ void sample_setup(const Homog& hm, float xt, float yt
   x0 = min(max(x0, 0), W - 1); x1 = min(max(x1, 0), W - 1);
   y0 = min(max(y0, 0), Hh - 1); y1 = min(max(y1, 0), Hh - 1);
   t.x0f = (float)x0; t.x1f = (float)x1; t.y0f = (float)y0; t.y1f = (float)y1;
-  t.wa = (t.x1f - x) * (t.y1f - y);
-  t.wb = (t.x1f - x) * (y - t.y0f);
-  t.wc = (x - t.x0f) * (t.y1f - y);
-  t.wd = (x - t.x0f) * (y - t.y0f);
+  t.wa = __fmul_rn(t.x1f - x, t.y1f - y);
+  t.wb = __fmul_rn(t.x1f - x, y - t.y0f);
+  t.wc = __fmul_rn(x - t.x0f, t.y1f - y);
+  t.wd = __fmul_rn(x - t.x0f, y - t.y0f);
   t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
   t.x = x; t.y = y; t.xn = xn; t.yn = yn; t.ts = ts;
+}
+
+// ((wa*Ia + wb*Ib) + wc*Ic) + wd*Id with every product and sum rounded separately — the reference evaluates
+// four tf.multiply and one add_n (tf_spatial_transformer.py:134-138), and the "black border" of out-of-range
+// samples relies on wa*Ia == -(wc*Ic) cancelling exactly; a fused multiply-add would leave ulp(w*I) residues.
+__device__ __forceinline__ float bilinear_rn(const Tap& t, float Ia, float Ib, float Ic, float Id) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.wa, Ia), __fmul_rn(t.wb, Ib)), __fmul_rn(t.wc, Ic)), __fmul_rn(t.wd, Id));
 }
 
 template <int C>
@@ -80,7 +87,7 @@ __device__ __forceinline__ float sample_gray(const float* __restrict__ img, cons
   for (int c = 0; c < C; ++c) {
     const float Ia = __ldg(img + (size_t)t.i00 * C + c), Ib = __ldg(img + (size_t)t.i10 * C + c);
     const float Ic = __ldg(img + (size_t)t.i01 * C + c), Id = __ldg(img + (size_t)t.i11 * C + c);
-    acc += ((t.wa * Ia + t.wb * Ib) + t.wc * Ic) + t.wd * Id;       // add_n order, then reduce_mean over C
+    acc = __fadd_rn(acc, bilinear_rn(t, Ia, Ib, Ic, Id));            // then reduce_mean over C (homography_model.py:263)
   }
   return C == 1 ? acc : acc / (float)C;
 }
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(256) transformer_kernel(const float* __restric
     for (int ch = 0; ch < C; ++ch) {
       const float Ia = __ldg(img + (size_t)t.i00 * C + ch), Ib = __ldg(img + (size_t)t.i10 * C + ch);
       const float Ic = __ldg(img + (size_t)t.i01 * C + ch), Id = __ldg(img + (size_t)t.i11 * C + ch);
-      dst[ch] = ((t.wa * Ia + t.wb * Ib) + t.wc * Ic) + t.wd * Id;
+      dst[ch] = bilinear_rn(t, Ia, Ib, Ic, Id);
     }
   }
 }
