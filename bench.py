@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — patch-pairs/s of the train step (BASELINE.json configs[1]: synthetic rho=45, 128x128 2-channel patches,
+per-GPU batch 128, loss_type=h_loss, Adam lr 5e-4), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W                      # our CUDA path (default numeric mode: see --numeric)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                               # the restated reference (oracle/) on the host CPU
+
+A step = one full pass of the hot path over one batch: regressor forward (dropout on), h4p losses, DLT, fused warp +
+all six photometric diagnostics (the reference fetches them every step, homography_CNN_synthetic.py:345), backward of
+h_loss, gradient allreduce (N > 1), TF-Adam update.  `value` is timed with inputs resident in HBM; `e2e` goes through
+the host-facing HostStepper API with pinned host inputs (H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "patch-pairs/sec (128x128) per train step"
+PER_GPU_BATCH = 128
+# MACs per pair of each conv layer's forward
+CONV_MACS = [18.87e6, 603.98e6, 150.99e6, 150.99e6, 75.50e6, 150.99e6, 37.75e6, 37.75e6]
+FWD_FLOP_PER_PAIR = 2.5208e9
+TRAIN_FLOP_PER_PAIR = 7.525e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--numeric", default=os.environ.get("UDH_NUMERIC", "auto"), choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--loss_type", default="h_loss")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_pairs_per_s(sample_b, steps, warmup, loss_type):
+    """The restated reference (oracle/, PyTorch-CPU fp32, all host threads) on a bounded sample of the workload."""
+    import torch
+    from oracle import oracle as O
+    from unsuperviseddeephomographyral2018_b200 import params as P
+    torch.set_num_threads(os.cpu_count() or 1)
+    specs = P.param_specs()
+    flat = torch.tensor(P.init_flat(0))
+    m, v = torch.zeros_like(flat), torch.zeros_like(flat)
+    batch = O.make_batch(0, sample_b)
+    g = torch.Generator().manual_seed(0)
+    s = 128 // 8
+    times = []
+    for i in range(warmup + steps):
+        keep = (torch.bernoulli(torch.full((sample_b, s, s, 128), 0.5), generator=g), torch.bernoulli(torch.full((sample_b, 1024), 0.5), generator=g))
+        t0 = time.perf_counter()
+        flat, m, v, out, _ = O.train_step(flat, m, v, i, batch, specs, loss_type=loss_type, lr=5e-4, keep_masks=keep)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return sample_b * len(times) / tot, tot / len(times) * 1e3, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = 4
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, ms, cores = cpu_oracle_pairs_per_s(sample_b, steps, warmup, args.loss_type)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "1-GPU train: synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s" % args.loss_type,
+                   "sample": "each step = %d pairs of the 128-pair batch on the host CPU" % sample_b},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d pairs/step x %d steps, oracle/ (PyTorch-CPU fp32 restatement; the TF1 reference cannot be installed here)" % (sample_b, steps)},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from unsuperviseddeephomographyral2018_b200 import _lib, engine, synthetic, trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    numeric = args.numeric
+    if numeric == "auto":
+        numeric = "bf16" if _lib.lib.udh_cnn_workspace_bytes(PER_GPU_BATCH, 128, _lib.NUMERIC_BF16) and _bf16_available(_lib) else "fp32"
+    B = PER_GPU_BATCH
+    eng = engine.HomographyEngine(B, numeric=numeric, seed=0, loss_type=args.loss_type, lr=5e-4, device=dev, process_group=pg, world_size=world)
+    nb = 3
+    batches = [synthetic.make_batch(B, seed=1000 * rank + i, device=dev) for i in range(nb)]
+    W, K = max(3, args.warmup), max(1, args.steps)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        eng.train_step(batches[i % nb])
+    barrier()
+    _lib.lib.udh_prof_enable(1); _lib.lib.udh_prof_reset()
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = _lib.lib.udh_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        eng.train_step(batches[i % nb])
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.lib.udh_launch_count() - launches0
+    phases = _lib.prof_read_all()
+    _lib.lib.udh_prof_enable(0)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = B * world * K / (ms_total * 1e-3)
+
+    # ---- end to end through the host-facing API (pinned host inputs, H2D + D2H every step) ----
+    e2e = None
+    if not args.no_e2e:
+        host = [trainer.pin_batch(b) for b in batches]
+        stepper = trainer.HostStepper(eng)
+        for i in range(3):
+            stepper.step(host[i % nb])
+        stepper.flush(); barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            stepper.step(host[i % nb])
+        last = stepper.flush()
+        e1.record(); barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ms_e = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms_e, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t[0].item())
+        e2e = {"value": B * world * K / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": stepper.h2d_bytes * world,
+               "d2h_bytes_per_step": stepper.d2h_bytes * world, "ms_per_step": ms_e / K, "wall_ms_per_step": float(t[1].item()) / K,
+               "api": "trainer.HostStepper.step(pinned post-dataloader tensors)", "last_h_loss": last["h_loss"] if last else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    # ---- roofline of the dominant kernel (by measured share of the step) ----
+    roof = None
+    if phases:
+        top = max(phases.items(), key=lambda kv: kv[1][0])
+        name, (tms, cnt) = top
+        per_launch_ms = tms / cnt
+        if name.startswith("conv"):
+            layer = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv4_1", "conv4_2"].index(name.split(".")[0])
+            flops = 2.0 * CONV_MACS[layer] * B
+            ach = flops / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peaks["source"] + ", sustained bf16", "ms_per_launch": per_launch_ms,
+                    "share_of_step": tms / K / ms_step}
+        elif name == "adam":
+            byts = 28.0 * 34192264
+            ach = byts / (per_launch_ms * 1e-3) / 1e9
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": peaks["source"], "ms_per_launch": per_launch_ms, "share_of_step": tms / K / ms_step}
+        else:
+            roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
+                    "ms_per_launch": per_launch_ms, "share_of_step": tms / K / ms_step}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sb = 8
+        v, ms_cpu, cores = cpu_oracle_pairs_per_s(sb, 2, 1, args.loss_type)
+        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": "%d-pair sample of the 128-pair batch, 1 warm-up + 2 timed train steps of oracle/ (PyTorch-CPU fp32 restatement)" % sb}
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": numeric, "data": "synthetic",
+        "config": {"workload": "1-GPU train: synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s (BASELINE configs[1])" % args.loss_type,
+                   "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world, "numeric_mode": numeric,
+                   "dropout": "on (keep 0.5)", "optimizer": "TF-Adam lr 5e-4 staircase",
+                   "l2_policy": "inputs larger than L2: %d rotating batches, 135 MB of inputs + ~1.7 GB of activations touched per step (L2 = 126 MB)" % nb},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "tflops_algorithmic": TRAIN_FLOP_PER_PAIR * B * world / (ms_step * 1e-3) / 1e12,
+        "phases_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _bf16_available(_lib):
+    """The tensor-core mode is the default when this build carries it (probe: tiny forward returns OK, not UDH_ENOSUP)."""
+    import ctypes
+    import torch
+    try:
+        B = 2
+        ws_bytes = _lib.lib.udh_cnn_workspace_bytes(B, 128, _lib.NUMERIC_BF16)
+        ws = torch.empty(ws_bytes, device="cuda", dtype=torch.uint8)
+        p = torch.zeros(_lib.lib.udh_param_total_floats(128), device="cuda")
+        x = torch.zeros(B, 128, 128, device="cuda"); h = torch.zeros(B, 8, device="cuda")
+        rc = _lib.lib.udh_cnn_fwd(ctypes.c_void_p(p.data_ptr()), ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(x.data_ptr()),
+                                  ctypes.c_void_p(h.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes, B, 128, 0, 0, _lib.NUMERIC_BF16,
+                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return rc == 0
+    except Exception:
+        return False
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

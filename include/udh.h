@@ -141,6 +141,18 @@ size_t udh_param_total_floats(int P);
 int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                   float eps, float grad_scale, int zero_grad, void* stream);
 
+/* ---- instrumentation read by bench.py -------------------------------------------------------------------------
+ * udh_launch_count: kernels this library has launched in this process (monotonic).
+ * udh_prof_*: when enabled, every tagged phase is bracketed by CUDA events recorded on the launching stream;
+ * udh_prof_read synchronises on them and returns the accumulated device time and the number of brackets.
+ * Must be off while a stream is being captured into a CUDA graph. */
+unsigned long long udh_launch_count(void);
+int udh_prof_enable(int on);
+int udh_prof_reset(void);
+int udh_prof_num_tags(void);
+const char* udh_prof_tag_name(int tag);
+int udh_prof_read(int tag, float* total_ms, int* count);
+
 #ifdef __cplusplus
 }
 #endif

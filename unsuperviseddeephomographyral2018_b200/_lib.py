@@ -2,7 +2,7 @@
 and if that is impossible the import fails loudly."""
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
 
 from . import build_ext
 
@@ -42,6 +42,12 @@ SIGNATURES = {
     "udh_param_total_floats": (c_size_t, [c_int]),
     "udh_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_void_p]),
+    "udh_launch_count": (c_ulonglong, []),
+    "udh_prof_enable": (c_int, [c_int]),
+    "udh_prof_reset": (c_int, []),
+    "udh_prof_num_tags": (c_int, []),
+    "udh_prof_tag_name": (c_char_p, [c_int]),
+    "udh_prof_read": (c_int, [c_int, POINTER(c_float), POINTER(c_int)]),
 }
 
 
@@ -71,3 +77,14 @@ def check(rc, what=""):
 def require_device():
     if not lib.udh_device_available():
         raise UdhError("no CUDA device: libudh has no CPU fallback (the CPU oracle lives in oracle/ and is test-only)")
+
+
+def prof_read_all():
+    """{tag name: (total_ms, count)} of the library's per-phase CUDA-event timers (non-empty phases only)."""
+    out = {}
+    for t in range(lib.udh_prof_num_tags()):
+        ms, n = c_float(), c_int()
+        check(lib.udh_prof_read(t, ctypes.byref(ms), ctypes.byref(n)), "udh_prof_read")
+        if n.value:
+            out[lib.udh_prof_tag_name(t).decode()] = (ms.value, n.value)
+    return out

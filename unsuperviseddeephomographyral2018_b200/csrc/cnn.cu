@@ -141,12 +141,16 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
     const float* cur1 = I2;
     for (int i = 0; i < 8; ++i) {
       const int s = P / kConv[i].div;
-      TRY(conv3x3_simt(cur0, cur1, params + PL.off[2 * i], params + PL.off[2 * i + 1], nullptr, at<float>(ws, L.act[i]), B, s,
-                       s, kConv[i].cin, kConv[i].cout, 1, st));
+      {
+        ProfScope ps(PROF_CONV_FWD0 + i, st);
+        TRY(conv3x3_simt(cur0, cur1, params + PL.off[2 * i], params + PL.off[2 * i + 1], nullptr, at<float>(ws, L.act[i]), B,
+                         s, s, kConv[i].cin, kConv[i].cout, 1, st));
+      }
       cur0 = at<float>(ws, L.act[i]);
       cur1 = nullptr;
       if (i == 1 || i == 3 || i == 5) {
         const int pi = 8 + i / 2;
+        ProfScope ps(PROF_POOL_FWD, st);
         TRY(maxpool2x2_fwd(cur0, at<float>(ws, L.act[pi]), B, s, s, kConv[i].cout, st));
         cur0 = at<float>(ws, L.act[pi]);
       }
@@ -155,10 +159,12 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
   // dropout after conv4_2 (homography_model.py:119-121), flatten NHWC (:124)
   const float* feat_in = at<float>(ws, L.act[7]);
   if (train) {
+    ProfScope ps(PROF_ELTWISE, st);
     TRY(dropout_fwd(feat_in, at<float>(ws, L.a4d), at<uint8_t>(ws, L.mask1), (size_t)B * feat, seed, 1, st));
     feat_in = at<float>(ws, L.a4d);
   }
   // fc1 + ReLU + dropout (:126-129): split-K SGEMM into a zeroed accumulator, then the fused epilogue
+  ProfScope ps_fc(PROF_FC_FWD, st);
   UDH_CUDA(cudaMemsetAsync(at<float>(ws, L.fc1_acc), 0, (size_t)B * 1024 * 4, st));
   TRY(sgemm_simt(feat_in, feat, 1, params + PL.off[16], 1024, 1, at<float>(ws, L.fc1_acc), 1024, B, 1024, feat,
                  B <= 256 ? 16 : 4, 0, st));
@@ -187,6 +193,7 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
   const float* feat_in = train ? at<float>(ws, L.a4d) : at<float>(ws, L.act[7]);
 
   // fc2
+  prof_begin(PROF_FC_BWD, st);
   TRY(sgemm_simt(fc1d, 1, 1024, dh4p, 8, 1, grads + PL.off[18], 8, 1024, 8, B, 1, 1, st));          // dW2 += fc1d^T . dh4p
   TRY(colsum_accum(dh4p, grads + PL.off[19], B, 8, st));
   TRY(sgemm_simt(dh4p, 8, 1, params + PL.off[18], 1, 8, dfc1, 1024, B, 1024, 8, 1, 0, st));          // dfc1d = dh4p . W2^T
@@ -196,6 +203,7 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
   TRY(colsum_accum(dfc1, grads + PL.off[17], B, 1024, st));
   TRY(sgemm_simt(dfc1, 1024, 1, params + PL.off[16], 1, 1024, gA, feat, B, feat, 1024, 1, 0, st));   // dx = dfc1 . W1^T
   TRY(drop_relu_bwd(gA, train ? at<uint8_t>(ws, L.mask1) : nullptr, at<float>(ws, L.act[7]), (size_t)B * feat, st));
+  prof_end(PROF_FC_BWD, st);
 
   if (numeric_mode == UDH_NUMERIC_BF16) {
     return tc_cnn_bwd_convs(params, PL.off, I1, I2, grads, gA, gB, ws, L.act, L.tc, B, P, st);
@@ -213,16 +221,23 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
     if (i == 0) { x0 = I1; x1 = I2; }
     else if (i == 2 || i == 4 || i == 6) x0 = at<float>(ws, L.act[8 + (i - 2) / 2]);
     else x0 = at<float>(ws, L.act[i - 1]);
-    TRY(wgrad3x3_simt(x0, x1, g, grads + PL.off[2 * i], grads + PL.off[2 * i + 1], B, s, s, cin, cout, st));
+    {
+      ProfScope ps(PROF_CONV_WGRAD0 + i, st);
+      TRY(wgrad3x3_simt(x0, x1, g, grads + PL.off[2 * i], grads + PL.off[2 * i + 1], B, s, s, cin, cout, st));
+    }
     if (i == 0) break;
-    TRY(rotate_weights(params + PL.off[2 * i], wrot, cin, cout, st));
     const bool below_is_pool = (i == 2 || i == 4 || i == 6);
-    // dgrad: conv over g with the rotated kernel; ReLU mask of the layer below fused unless a pool sits between
-    TRY(conv3x3_simt(g, nullptr, wrot, nullptr, below_is_pool ? nullptr : at<float>(ws, L.act[i - 1]), other, B, s, s, cout,
-                     cin, 0, st));
+    {
+      ProfScope ps(PROF_CONV_DGRAD0 + i, st);
+      TRY(rotate_weights(params + PL.off[2 * i], wrot, cin, cout, st));
+      // dgrad: conv over g with the rotated kernel; ReLU mask of the layer below fused unless a pool sits between
+      TRY(conv3x3_simt(g, nullptr, wrot, nullptr, below_is_pool ? nullptr : at<float>(ws, L.act[i - 1]), other, B, s, s,
+                       cout, cin, 0, st));
+    }
     { float* t = g; g = other; other = t; }
     if (below_is_pool) {
       // g = d pool_out  ->  d (pre-activation of conv i-1), arg-max routing + ReLU mask
+      ProfScope ps(PROF_POOL_BWD, st);
       TRY(maxpool2x2_bwd(at<float>(ws, L.act[i - 1]), g, other, B, 2 * s, 2 * s, cin, st));
       { float* t = g; g = other; other = t; }
     }

@@ -11,7 +11,25 @@ namespace udh {
 
 void set_error(const char* fmt, ...);
 
+// ---- in-library instrumentation (bench.py reads it): kernel-launch counter and per-phase CUDA-event timers ----
+enum ProfTag {
+  PROF_CONV_FWD0 = 0,    // +layer (0..7)
+  PROF_CONV_DGRAD0 = 8,  // +layer
+  PROF_CONV_WGRAD0 = 16, // +layer
+  PROF_POOL_FWD = 24, PROF_POOL_BWD, PROF_FC_FWD, PROF_FC_BWD, PROF_DLT, PROF_WARP_FWD, PROF_WARP_BWD, PROF_SSIM,
+  PROF_H4P_LOSS, PROF_ADAM, PROF_ELTWISE, PROF_TC_PREP, PROF_NUM_TAGS
+};
+extern unsigned long long g_launches;
+void prof_begin(int tag, cudaStream_t st);
+void prof_end(int tag, cudaStream_t st);
+struct ProfScope {
+  int tag; cudaStream_t st;
+  ProfScope(int t, cudaStream_t s) : tag(t), st(s) { prof_begin(tag, st); }
+  ~ProfScope() { prof_end(tag, st); }
+};
+
 inline int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(128) dlt_bwd_kernel(const float* __restrict__ 
 extern "C" int udh_dlt_fwd(const float* pts1, const float* h4p, float* H, int B, void* stream) {
   UDH_REQUIRE(pts1 && h4p && H && B >= 0, "udh_dlt_fwd: null pointer or negative batch");
   if (B == 0) return UDH_OK;
+  udh::ProfScope ps(udh::PROF_DLT, udh::as_stream(stream));
   udh::dlt_fwd_kernel<<<(B + 3) / 4, 128, 0, udh::as_stream(stream)>>>(pts1, h4p, H, B);
   return udh::check_launch("udh_dlt_fwd");
 }
@@ -135,6 +136,7 @@ extern "C" int udh_dlt_bwd(const float* pts1, const float* h4p, const float* H, 
                            void* stream) {
   UDH_REQUIRE(pts1 && h4p && H && dH && dh4p && B >= 0, "udh_dlt_bwd: null pointer or negative batch");
   if (B == 0) return UDH_OK;
+  udh::ProfScope ps(udh::PROF_DLT, udh::as_stream(stream));
   udh::dlt_bwd_kernel<<<(B + 3) / 4, 128, 0, udh::as_stream(stream)>>>(pts1, h4p, H, dH, dh4p, B);
   return udh::check_launch("udh_dlt_bwd");
 }

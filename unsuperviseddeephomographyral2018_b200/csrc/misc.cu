@@ -14,6 +14,41 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+unsigned long long g_launches = 0;
+
+namespace {
+const char* kTagNames[PROF_NUM_TAGS] = {
+    "conv1_1.fwd", "conv1_2.fwd", "conv2_1.fwd", "conv2_2.fwd", "conv3_1.fwd", "conv3_2.fwd", "conv4_1.fwd", "conv4_2.fwd",
+    "conv1_1.dgrad", "conv1_2.dgrad", "conv2_1.dgrad", "conv2_2.dgrad", "conv3_1.dgrad", "conv3_2.dgrad", "conv4_1.dgrad", "conv4_2.dgrad",
+    "conv1_1.wgrad", "conv1_2.wgrad", "conv2_1.wgrad", "conv2_2.wgrad", "conv3_1.wgrad", "conv3_2.wgrad", "conv4_1.wgrad", "conv4_2.wgrad",
+    "pool.fwd", "pool.bwd", "fc.fwd", "fc.bwd", "dlt", "warp_loss.fwd", "warp_loss.bwd", "ssim", "h4p_loss", "adam", "eltwise", "tc_prep"};
+constexpr int kMaxPairs = 2048;
+struct TagState { cudaEvent_t ev[kMaxPairs][2]; int created = 0, used = 0; bool open = false; };
+bool g_prof_on = false;
+TagState* g_tags = nullptr;
+}  // namespace
+
+void prof_begin(int tag, cudaStream_t st) {
+  if (!g_prof_on || tag < 0 || tag >= PROF_NUM_TAGS) return;
+  TagState& t = g_tags[tag];
+  if (t.used >= kMaxPairs) return;
+  if (t.used >= t.created) {
+    if (cudaEventCreate(&t.ev[t.created][0]) != cudaSuccess || cudaEventCreate(&t.ev[t.created][1]) != cudaSuccess) return;
+    ++t.created;
+  }
+  cudaEventRecord(t.ev[t.used][0], st);
+  t.open = true;
+}
+
+void prof_end(int tag, cudaStream_t st) {
+  if (!g_prof_on || tag < 0 || tag >= PROF_NUM_TAGS) return;
+  TagState& t = g_tags[tag];
+  if (!t.open) return;
+  cudaEventRecord(t.ev[t.used][1], st);
+  ++t.used;
+  t.open = false;
+}
+
 // h_loss = sqrt(mean_{B x 8}(pred-gt)^2) (homography_model.py:288); test metrics (:274-281):
 // batch_h_loss_b = sqrt(mean_8 (pred-gt)^2), identity_b = sqrt(mean_8 gt^2), failure = batch >= identity,
 // bounded = mean_b(failure ? identity : batch).  One CTA; B is small (<= a few thousand).
@@ -84,9 +119,43 @@ extern "C" int udh_device_available(void) {
   return n > 0 ? 1 : 0;
 }
 
+extern "C" unsigned long long udh_launch_count(void) { return udh::g_launches; }
+
+extern "C" int udh_prof_enable(int on) {
+  if (on && !udh::g_tags) udh::g_tags = new udh::TagState[udh::PROF_NUM_TAGS];
+  udh::g_prof_on = on != 0;
+  return UDH_OK;
+}
+
+extern "C" int udh_prof_reset(void) {
+  if (udh::g_tags)
+    for (int i = 0; i < udh::PROF_NUM_TAGS; ++i) { udh::g_tags[i].used = 0; udh::g_tags[i].open = false; }
+  return UDH_OK;
+}
+
+extern "C" int udh_prof_num_tags(void) { return udh::PROF_NUM_TAGS; }
+
+extern "C" const char* udh_prof_tag_name(int tag) { return (tag >= 0 && tag < udh::PROF_NUM_TAGS) ? udh::kTagNames[tag] : ""; }
+
+extern "C" int udh_prof_read(int tag, float* total_ms, int* count) {
+  UDH_REQUIRE(tag >= 0 && tag < udh::PROF_NUM_TAGS && total_ms && count, "udh_prof_read: bad arguments");
+  *total_ms = 0.f; *count = 0;
+  if (!udh::g_tags) return UDH_OK;
+  udh::TagState& t = udh::g_tags[tag];
+  for (int i = 0; i < t.used; ++i) {
+    float ms = 0.f;
+    UDH_CUDA(cudaEventSynchronize(t.ev[i][1]));
+    UDH_CUDA(cudaEventElapsedTime(&ms, t.ev[i][0], t.ev[i][1]));
+    *total_ms += ms;
+  }
+  *count = t.used;
+  return UDH_OK;
+}
+
 extern "C" int udh_h4p_loss(const float* pred, const float* gt, int B, float* metrics, float* per_sample, float* dpred,
                             void* stream) {
   UDH_REQUIRE(pred && gt && metrics && B >= 1, "udh_h4p_loss: bad arguments");
+  udh::ProfScope ps(udh::PROF_H4P_LOSS, udh::as_stream(stream));
   udh::h4p_loss_kernel<<<1, 256, 0, udh::as_stream(stream)>>>(pred, gt, B, metrics, per_sample, dpred);
   return udh::check_launch("udh_h4p_loss");
 }
@@ -99,6 +168,7 @@ extern "C" int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, f
   if (n == 0) return UDH_OK;
   const size_t n4 = n / 4;
   const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  udh::ProfScope ps(udh::PROF_ADAM, udh::as_stream(stream));
   udh::adam_kernel<<<blocks, 256, 0, udh::as_stream(stream)>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
                                                               beta1, beta2, eps, grad_scale, zero_grad);
   return udh::check_launch("udh_adam_step");

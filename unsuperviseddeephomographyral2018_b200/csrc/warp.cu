@@ -356,6 +356,7 @@ extern "C" int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, co
   UDH_REQUIRE(pred || (I2 && sums), "udh_warp_loss_fwd: nothing to compute (no pred, no I2+sums)");
   if (B == 0) return UDH_OK;
   dim3 grid(((pw + 127) / 128) * ((ph + 7) / 8), B);
+  ProfScope ps(PROF_WARP_FWD, as_stream(stream));
   if (C == 3)
     warp_loss_fwd_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
   else
@@ -374,6 +375,7 @@ extern "C" int udh_warp_loss_bwd(const float* I, int C, int img_h, int img_w, co
   UDH_REQUIRE(loss_type != UDH_LOSS_REC || sums, "udh_warp_loss_bwd: REC needs the forward sums");
   if (B == 0) return UDH_OK;
   cudaStream_t st = as_stream(stream);
+  ProfScope ps(PROF_WARP_BWD, st);
   UDH_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 9 * (size_t)B, st));
   dim3 grid(((pw + 127) / 128) * ((ph + 7) / 8), B);
   const double n_total = (double)B * pw * ph;
@@ -393,6 +395,7 @@ extern "C" int udh_ssim_fwd(const float* pred, const float* I2, int pw, int ph, 
   if (B == 0) return UDH_OK;
   const int n = (pw - 2) * (ph - 2);
   dim3 grid(min((n + 255) / 256, 64), B);
+  ProfScope ps(PROF_SSIM, as_stream(stream));
   ssim_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, I2, pw, ph, sums);
   return check_launch("udh_ssim_fwd");
 }
