@@ -118,6 +118,8 @@ int udh_h4p_loss(const float* pred, const float* gt, int B, float* metrics, floa
  * and fc1 with masks drawn from `seed` (kept in the workspace for the backward and readable with
  * udh_cnn_dropout_masks).  The workspace keeps the activations between fwd and bwd. */
 size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode);
+/* call once after allocating the workspace (zeroes the borders of the padded bf16 streams of UDH_NUMERIC_BF16). */
+int udh_cnn_workspace_init(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void* stream);
 int udh_cnn_fwd(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes, int B,
                 int P, int train, uint64_t seed, int numeric_mode, void* stream);
 /* dh4p[B,8] -> grads (ACCUMULATED into the flat buffer: caller zeroes it once per step). */
@@ -152,6 +154,15 @@ int udh_prof_reset(void);
 int udh_prof_num_tags(void);
 const char* udh_prof_tag_name(int tag);
 int udh_prof_read(int tag, float* total_ms, int* count);
+
+/* ---- debug / test entry points of the tensor-core path ---------------------------------------------------------
+ * udh_debug_umma_probe: hardware probe of the TMA / tcgen05 descriptor conventions (csrc/tc_probe.cu).
+ * udh_debug_tc_conv: ONE tcgen05 3x3 convolution on fp32 NHWC tensors (pads + casts to bf16 internally), so tests can
+ * compare the tensor-core kernel with a reference convolution layer by layer; dgrad != 0 runs the mirrored kernel. */
+int udh_debug_umma_probe(const void* A, int a_rows, const void* B, int b_rows, float* out, int mode, int use_bo, void* stream);
+size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout);
+int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W,
+                      int cin, int cout, int relu, int dgrad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -103,6 +103,14 @@ extern "C" size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode) {
   return Workspace(B, P, numeric_mode).total;
 }
 
+extern "C" int udh_cnn_workspace_init(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void* stream) {
+  TRY(check_cnn_args("udh_cnn_workspace_init", B, P, numeric_mode));
+  Workspace L(B, P, numeric_mode);
+  UDH_REQUIRE(ws && ws_bytes >= L.total, "udh_cnn_workspace_init: bad workspace");
+  if (numeric_mode == UDH_NUMERIC_BF16) return tc_workspace_init(ws, L.tc, B, P, as_stream(stream));
+  return UDH_OK;
+}
+
 extern "C" int udh_cnn_dropout_masks(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, const uint8_t** mask_conv4,
                                      const uint8_t** mask_fc1) {
   TRY(check_cnn_args("udh_cnn_dropout_masks", B, P, numeric_mode));

@@ -1,6 +1,8 @@
 // Launchers of the regressor's building blocks (Row C).  fp32 CUDA-core kernels live in cnn_simt.cu; the
 // tcgen05 tensor-core path lives in conv_tc.cu.  All tensors NHWC fp32 unless noted.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace udh {
@@ -11,6 +13,10 @@ namespace udh {
 // whose forward output is mask_src — used when this kernel runs as a dgrad).
 int conv3x3_simt(const float* in0, const float* in1, const float* w, const float* bias, const float* mask_src,
                  float* out, int B, int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
+
+// same convolution, output written as a zero-bordered bf16 stream [B,H+2,W+2,Cout] (interior only)
+int conv3x3_simt_bf16out(const float* in0, const float* in1, const float* w, const float* bias, __nv_bfloat16* out_pad, int B,
+                         int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
 
 // dW[ky,kx,ci,co] += sum_{n,y,x} x[n,y+ky-1,x+kx-1,ci] * g[n,y,x,co];  db[co] += sum g   (atomic accumulation)
 int wgrad3x3_simt(const float* x0, const float* x1, const float* g, float* dW, float* db, int B, int H, int W,

@@ -1,20 +1,369 @@
-// placeholder until the tcgen05 path lands: the BF16 numeric mode reports UDH_ENOSUP.
+// UDH_NUMERIC_BF16: the regressor's conv stack on tcgen05 tensor cores (see conv_tc_kernels.cuh for the kernel design).
+// Activations and activation gradients are zero-bordered NHWC bf16 ("padded streams"); parameters, parameter gradients,
+// the fully connected head and all reductions stay fp32.
 #include "conv_tc.cuh"
+
+#include "cnn_kernels.cuh"
+#include "conv_tc_kernels.cuh"
 
 namespace udh {
 
-size_t tc_workspace_bytes(int, int, int) { return 0; }
+namespace {
 
-int tc_cnn_fwd_convs(const float*, const size_t*, const float*, const float*, void*, const size_t*, size_t, int, int,
-                     cudaStream_t) {
-  set_error("UDH_NUMERIC_BF16 is not available in this build");
+struct ConvSpec { int cin, cout, div; };
+const ConvSpec kConv[8] = {{2, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 2}, {64, 128, 4}, {128, 128, 4}, {128, 128, 8}, {128, 128, 8}};
+
+inline size_t al256(size_t n) { return (n + 255) / 256 * 256; }
+inline unsigned grid1d(size_t want, size_t cap) { return (unsigned)(want < cap ? (want ? want : 1) : cap); }
+
+// byte offsets inside the tensor-core region of the workspace
+struct TcLayout {
+  size_t P[11];      // padded bf16 activations: 0..7 conv outputs, 8..10 pool outputs
+  size_t G[11];      // padded bf16 gradients w.r.t. the same tensors (pre-activation for convs)
+  size_t numel[11];  // padded element counts
+  size_t wf[8], wd[8];   // packed bf16 weights, forward / dgrad (rotated)
+  size_t total;
+  TcLayout(int B, int P_) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
+    for (int i = 0; i < 8; ++i) {
+      const size_t s = P_ / kConv[i].div + 2;
+      numel[i] = (size_t)B * s * s * kConv[i].cout;
+    }
+    numel[8] = (size_t)B * (P_ / 2 + 2) * (P_ / 2 + 2) * 64;
+    numel[9] = (size_t)B * (P_ / 4 + 2) * (P_ / 4 + 2) * 64;
+    numel[10] = (size_t)B * (P_ / 8 + 2) * (P_ / 8 + 2) * 128;
+    for (int i = 0; i < 11; ++i) P[i] = take(numel[i] * 2);
+    for (int i = 0; i < 11; ++i) G[i] = take(numel[i] * 2);
+    for (int i = 0; i < 8; ++i) { wf[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); wd[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); }
+    total = o;
+  }
+};
+
+template <typename T>
+inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
+
+#define TRY(call)                    \
+  do {                               \
+    int rc__ = (call);               \
+    if (rc__ != UDH_OK) return rc__; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------- small kernels
+// dst[tap][cb][n][k] bf16 <- fp32 HWIO w[tap][ci][co].
+//   forward: n = co, k-channel = ci.   dgrad: n = ci, k-channel = co, tap mirrored (w[8-tap]).
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cin, int Cout, int dgrad) {
+  const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;      // contraction channels, output channels of the packed conv
+  const int CBk = K / 64;
+  const int total = 9 * K * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 63;
+    int r = i >> 6;
+    const int n = r % N; r /= N;
+    const int cb = r % CBk;
+    const int tap = r / CBk;
+    const int kc = cb * 64 + k;
+    const float v = dgrad ? w[((size_t)(8 - tap) * Cin + n) * Cout + kc] : w[((size_t)tap * Cin + kc) * Cout + n];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// fp32 [B,H,W,C] -> bf16 padded [B,H+2,W+2,C] interior (borders untouched = zero)
+__global__ void pad_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C) {
+  const int C4 = C >> 2;
+  const size_t total = (size_t)B * H * W * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t r = i / C4;
+    const int x = r % W; r /= W;
+    const int y = r % H;
+    const int n = r / H;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst + (((size_t)n * (H + 2) + y + 1) * (W + 2) + x + 1) * C + c4 * 4) = pk;
+  }
+}
+
+// bf16 padded -> fp32 [B,H,W,C]
+__global__ void unpad_cast_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int B, int H, int W, int C) {
+  const int C4 = C >> 2;
+  const size_t total = (size_t)B * H * W * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = i % C4;
+    size_t r = i / C4;
+    const int x = r % W; r /= W;
+    const int y = r % H;
+    const int n = r / H;
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(src + (((size_t)n * (H + 2) + y + 1) * (W + 2) + x + 1) * C + c4 * 4));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&pk.x), b = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    f[2 * i] = __low2float(p); f[2 * i + 1] = __high2float(p);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// 2x2/2 max pool on padded bf16 streams: in [B,H+2,W+2,C] -> out [B,H/2+2,W/2+2,C]
+__global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+  const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
+  const size_t total = (size_t)B * OH * OW * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = i % C8;
+    size_t r = i / C8;
+    const int ox = r % OW; r /= OW;
+    const int oy = r % OH;
+    const int n = r / OH;
+    const __nv_bfloat16* p = in + (((size_t)n * (H + 2) + 2 * oy + 1) * (W + 2) + 2 * ox + 1) * C + c8 * 8;
+    float a[8], b[8], c[8], d[8], m[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + C)), b);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + (size_t)(W + 2) * C)), c);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p + (size_t)(W + 2) * C + C)), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    *reinterpret_cast<uint4*>(out + (((size_t)n * (OH + 2) + oy + 1) * (OW + 2) + ox + 1) * C + c8 * 8) = pack8(m);
+  }
+}
+
+// gradient routing of the above + ReLU mask of the producer (first arg-max in scan order, only where it is > 0)
+__global__ void pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ gout,
+                                     __nv_bfloat16* __restrict__ gin, int B, int H, int W, int C) {
+  const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
+  const size_t total = (size_t)B * OH * OW * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = i % C8;
+    size_t r = i / C8;
+    const int ox = r % OW; r /= OW;
+    const int oy = r % OH;
+    const int n = r / OH;
+    const size_t base = (((size_t)n * (H + 2) + 2 * oy + 1) * (W + 2) + 2 * ox + 1) * C + c8 * 8;
+    const size_t rowp = (size_t)(W + 2) * C;
+    float a[8], b[8], c[8], d[8], g[8], oa[8], ob[8], oc[8], od[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + C)), b);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + rowp)), c);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + rowp + C)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gout + (((size_t)n * (OH + 2) + oy + 1) * (OW + 2) + ox + 1) * C + c8 * 8)), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float m = a[j]; int k = 0;
+      if (b[j] > m) { m = b[j]; k = 1; }
+      if (c[j] > m) { m = c[j]; k = 2; }
+      if (d[j] > m) { m = d[j]; k = 3; }
+      const float v = m > 0.f ? g[j] : 0.f;
+      oa[j] = k == 0 ? v : 0.f; ob[j] = k == 1 ? v : 0.f; oc[j] = k == 2 ? v : 0.f; od[j] = k == 3 ? v : 0.f;
+    }
+    *reinterpret_cast<uint4*>(gin + base) = pack8(oa);
+    *reinterpret_cast<uint4*>(gin + base + C) = pack8(ob);
+    *reinterpret_cast<uint4*>(gin + base + rowp) = pack8(oc);
+    *reinterpret_cast<uint4*>(gin + base + rowp + C) = pack8(od);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------- launchers
+template <int N_OUT, int CB, int T, bool WRES>
+int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const __nv_bfloat16* mask_src,
+                __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, cudaStream_t st) {
+  tc::ConvGeom g;
+  g.B = B; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
+  g.Q = B * g.Hp * g.Wp;
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  const int tiles = (g.Q + 127) / 128;
+  g.num_items = (tiles + T - 1) / T;
+  g.abuf_rows = T * 128 + 2 * g.hh;
+  const int Cin = CB * 64;
+  CUtensorMap tmA128, tmAhh, tmW;
+  uint64_t dimsA[2] = {(uint64_t)Cin, (uint64_t)g.Q}, strA[2] = {2, (uint64_t)Cin * 2};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh};
+  TRY(tc::make_tmap_bf16(&tmA128, x, 2, dimsA, strA, box128));
+  TRY(tc::make_tmap_bf16(&tmAhh, x, 2, dimsA, strA, boxhh));
+  uint64_t dimsW[2] = {64, (uint64_t)9 * CB * N_OUT}, strW[2] = {2, 128};
+  uint32_t boxW[2] = {64, (uint32_t)N_OUT};
+  TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
+  const size_t smem = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows);
+  UDH_REQUIRE(smem <= 232448, "tc conv: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = g.num_items < sms ? g.num_items : sms;
+  kern<<<grid, 256, smem, st>>>(tmA128, tmAhh, tmW, g, bias, mask_src, out_bf, out_f32, relu);
+  return check_launch("tc_conv_kernel");
+}
+
+// one 3x3 conv on padded bf16 streams; (cin -> cout) selects the kernel instance
+int tc_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const __nv_bfloat16* mask_src,
+            __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, int cin, int cout, cudaStream_t st) {
+  if (cin == 64 && cout == 64) return launch_conv<64, 1, 2, true>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 64 && cout == 128) return launch_conv<128, 1, 1, true>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 128 && cout == 64) return launch_conv<64, 2, 2, false>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 128 && cout == 128) return launch_conv<128, 2, 2, false>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
+  set_error("tc_conv: unsupported channel combination %d -> %d", cin, cout);
   return UDH_ENOSUP;
 }
 
-int tc_cnn_bwd_convs(const float*, const size_t*, const float*, const float*, float*, float*, float*, void*, const size_t*,
-                     size_t, int, int, cudaStream_t) {
-  set_error("UDH_NUMERIC_BF16 is not available in this build");
-  return UDH_ENOSUP;
+int pack_weights(const float* w, __nv_bfloat16* dst, int cin, int cout, int dgrad, cudaStream_t st) {
+  const int total = 9 * cin * cout;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, dst, cin, cout, dgrad);
+  return check_launch("pack_weights");
+}
+int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t total = (size_t)B * H * W * (C / 4);
+  pad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
+  return check_launch("pad_cast");
+}
+int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t total = (size_t)B * H * W * (C / 4);
+  unpad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
+  return check_launch("unpad_cast");
+}
+int pool_fwd_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  pool_fwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, out, B, H, W, C);
+  return check_launch("pool_fwd_bf16");
+}
+int pool_bwd_bf16(const __nv_bfloat16* in, const __nv_bfloat16* gout, __nv_bfloat16* gin, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+  pool_bwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, gout, gin, B, H, W, C);
+  return check_launch("pool_bwd_bf16");
+}
+
+// input tensor index (into P / G) of conv layer i (i >= 1)
+inline int input_of(int i) { return (i == 2 || i == 4 || i == 6) ? 8 + (i - 2) / 2 : i - 1; }
+
+}  // namespace
+
+size_t tc_workspace_bytes(int B, int P, int numeric_mode) {
+  if (numeric_mode != UDH_NUMERIC_BF16) return 0;
+  return TcLayout(B, P).total;
+}
+
+int tc_workspace_init(void* ws, size_t tc_off, int B, int P, cudaStream_t st) {
+  TcLayout L(B, P);
+  // borders of every padded stream must be zero and are never written afterwards
+  UDH_CUDA(cudaMemsetAsync(at<char>(ws, tc_off), 0, L.total, st));
+  return UDH_OK;
+}
+
+int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, const float* I2, void* ws, const size_t* act_off,
+                     size_t tc_off, int B, int P, cudaStream_t st) {
+  TcLayout L(B, P);
+  char* tcw = at<char>(ws, tc_off);
+  auto Pb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.P[i]); };
+  {
+    ProfScope ps(PROF_TC_PREP, st);
+    for (int i = 1; i < 8; ++i)
+      TRY(pack_weights(params + poff[2 * i], reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), kConv[i].cin, kConv[i].cout, 0, st));
+  }
+  {
+    // conv1_1 (K = 18): fp32 CUDA-core kernel writing the padded bf16 stream directly
+    ProfScope ps(PROF_CONV_FWD0, st);
+    TRY(conv3x3_simt_bf16out(I1, I2, params + poff[0], params + poff[1], Pb(0), B, P, P, 2, 64, 1, st));
+  }
+  for (int i = 1; i < 8; ++i) {
+    const int s = P / kConv[i].div;
+    {
+      ProfScope ps(PROF_CONV_FWD0 + i, st);
+      TRY(tc_conv(Pb(input_of(i)), reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), params + poff[2 * i + 1], nullptr, Pb(i),
+                  i == 7 ? at<float>(ws, act_off[7]) : nullptr, 1, B, s, s, kConv[i].cin, kConv[i].cout, st));
+    }
+    if (i == 1 || i == 3 || i == 5) {
+      ProfScope ps(PROF_POOL_FWD, st);
+      TRY(pool_fwd_bf16(Pb(i), Pb(8 + i / 2), B, s, s, kConv[i].cout, st));
+    }
+  }
+  return UDH_OK;
+}
+
+int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, const float* I2, float* grads, float* gA, float* gB,
+                     void* ws, const size_t* act_off, size_t tc_off, int B, int P, cudaStream_t st) {
+  TcLayout L(B, P);
+  char* tcw = at<char>(ws, tc_off);
+  auto Pb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.P[i]); };
+  auto Gb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.G[i]); };
+  {
+    ProfScope ps(PROF_TC_PREP, st);
+    for (int i = 1; i < 8; ++i)
+      TRY(pack_weights(params + poff[2 * i], reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]), kConv[i].cin, kConv[i].cout, 1, st));
+    TRY(pad_cast(gA, Gb(7), B, P / 8, P / 8, 128, st));
+  }
+  for (int i = 7; i >= 0; --i) {
+    const int s = P / kConv[i].div;
+    const int cin = kConv[i].cin, cout = kConv[i].cout;
+    {
+      // weight gradient: interim path — fp32 CUDA-core wgrad on unpadded fp32 copies of the bf16 streams
+      ProfScope ps(PROF_CONV_WGRAD0 + i, st);
+      TRY(unpad_cast(Gb(i), gA, B, s, s, cout, st));
+      if (i == 0) {
+        TRY(wgrad3x3_simt(I1, I2, gA, grads + poff[0], grads + poff[1], B, s, s, cin, cout, st));
+      } else {
+        TRY(unpad_cast(Pb(input_of(i)), gB, B, s, s, cin, st));
+        TRY(wgrad3x3_simt(gB, nullptr, gA, grads + poff[2 * i], grads + poff[2 * i + 1], B, s, s, cin, cout, st));
+      }
+    }
+    if (i == 0) break;
+    const bool below_is_pool = (i == 2 || i == 4 || i == 6);
+    const int below = input_of(i);
+    {
+      ProfScope ps(PROF_CONV_DGRAD0 + i, st);
+      // dgrad = conv of G[i] with the mirrored kernel; ReLU mask of the layer below fused unless a pool sits between
+      TRY(tc_conv(Gb(i), reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]), nullptr, below_is_pool ? nullptr : Pb(below), Gb(below),
+                  nullptr, 0, B, s, s, cout, cin, st));
+    }
+    if (below_is_pool) {
+      ProfScope ps(PROF_POOL_BWD, st);
+      TRY(pool_bwd_bf16(Pb(i - 1), Gb(below), Gb(i - 1), B, 2 * s, 2 * s, cin, st));
+    }
+  }
+  return UDH_OK;
+}
+
+// Debug / test entry: one tensor-core conv layer on fp32 NHWC tensors (pads + casts internally).
+// x [B,H,W,cin], w HWIO [3,3,cin,cout], bias [cout] (nullable), out [B,H,W,cout]; scratch: device buffer of
+// udh_debug_tc_conv_scratch_bytes().  dgrad != 0 runs the mirrored-kernel convolution (cout -> cin channels).
+size_t tc_debug_scratch_bytes(int B, int H, int W, int cin, int cout) {
+  return al256((size_t)B * (H + 2) * (W + 2) * cin * 2) + al256((size_t)B * (H + 2) * (W + 2) * cout * 2) + al256((size_t)9 * cin * cout * 2);
+}
+
+int tc_debug_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W, int cin, int cout,
+                  int relu, int dgrad, cudaStream_t st) {
+  const int kin = dgrad ? cout : cin, kout = dgrad ? cin : cout;      // channels of the convolution actually run
+  char* s = reinterpret_cast<char*>(scratch);
+  __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(s);
+  __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(s + al256((size_t)B * (H + 2) * (W + 2) * kin * 2));
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(s + al256((size_t)B * (H + 2) * (W + 2) * kin * 2) + al256((size_t)B * (H + 2) * (W + 2) * kout * 2));
+  UDH_CUDA(cudaMemsetAsync(scratch, 0, tc_debug_scratch_bytes(B, H, W, cin, cout), st));
+  TRY(pad_cast(x, xp, B, H, W, kin, st));
+  TRY(pack_weights(w, wp, cin, cout, dgrad, st));
+  TRY(tc_conv(xp, wp, bias, nullptr, op, out, relu, B, H, W, kin, kout, st));
+  return UDH_OK;
 }
 
 }  // namespace udh
+
+extern "C" size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout) {
+  return udh::tc_debug_scratch_bytes(B, H, W, cin, cout);
+}
+
+extern "C" int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W,
+                                 int cin, int cout, int relu, int dgrad, void* stream) {
+  UDH_REQUIRE(x && w && out && scratch, "udh_debug_tc_conv: null pointer");
+  return udh::tc_debug_conv(x, w, bias, out, scratch, B, H, W, cin, cout, relu, dgrad, udh::as_stream(stream));
+}

@@ -7,6 +7,9 @@ namespace udh {
 // extra workspace the tensor-core path needs behind the fp32 carve-up (bf16 activations, packed weights, ...)
 size_t tc_workspace_bytes(int B, int P, int numeric_mode);
 
+// zero the padded streams once after the workspace is allocated (their borders are never written afterwards)
+int tc_workspace_init(void* ws, size_t tc_off, int B, int P, cudaStream_t st);
+
 // conv1_1 .. conv4_2 + the three max-pools; writes the fp32 activations the rest of the pipeline reads
 // (act_off[7]: conv4_2 output) and keeps bf16 copies for the backward.
 int tc_cnn_fwd_convs(const float* params, const size_t* param_off, const float* I1, const float* I2, void* ws,

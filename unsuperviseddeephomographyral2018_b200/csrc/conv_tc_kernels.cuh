@@ -1,0 +1,241 @@
+// tcgen05 implicit-GEMM 3x3 convolution over a flattened, zero-bordered NHWC bf16 activation ("padded stream").
+//
+// Layout.  An activation [B,H,W,C] is stored as [B][H+2][W+2][C] bf16 with zero borders; flattened, it is a matrix
+// X[Q = B*(H+2)*(W+2) positions][C].  With Wp = W+2, the input of tap (ky,kx) for output position q is simply row
+// q + (ky-1)*Wp + (kx-1): every tap is a ROW SHIFT of the same matrix, borders supply the zero padding, and images
+// never bleed into each other.  Outputs at border positions are computed but not stored (~3 % waste at W = 128).
+//
+// Kernel.  One persistent CTA per SM walks work items of T consecutive 128-position tiles:
+//   * TMA (SWIZZLE_128B) stages rows [q0-hh, q0+128T+hh) of X once per item into a linear smem buffer (per 64-channel
+//     block); all 9 taps are tcgen05 shared-memory descriptors whose START ADDRESS is shifted by whole 128-byte rows
+//     inside that buffer (the hardware swizzles on absolute smem address bits, so unaligned row starts need no
+//     base_offset — measured with tools/tc_probe.py).  L2->smem traffic is ~(1 + 2hh/128T)x the activation instead of 9x.
+//   * weights [tap][cblock][Cout][64] are either resident in smem (<= 144 KiB) or streamed through a small TMA ring,
+//     each streamed k-block being reused by the T tiles of the item (T accumulators in TMEM);
+//   * fp32 accumulators live in TMEM (2 sets x T tiles x Cout columns): the epilogue warps drain set b while the MMA
+//     thread fills set b^1 and the TMA thread prefetches the next item's rows.
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: epilogue (TMEM lane quarters).
+#pragma once
+#include "tc_common.cuh"
+
+namespace udh {
+namespace tc {
+
+struct ConvGeom {
+  int B, H, W, Hp, Wp;     // Hp = H+2, Wp = W+2
+  int Q;                   // B*Hp*Wp flattened positions
+  int hh;                  // halo rows staged on each side: round_up(Wp+1, 8)
+  int num_items;           // ceil(ceil(Q/128) / T)
+  int abuf_rows;           // T*128 + 2*hh
+};
+
+constexpr int kNumWStages = 3;
+
+template <int N_OUT, int CB, int T, bool WRES>
+struct ConvSmem {
+  static constexpr int kWBytesPerKb = N_OUT * 128;
+  static constexpr int kWBytes = WRES ? 9 * CB * kWBytesPerKb : kNumWStages * kWBytesPerKb;
+  static size_t bytes(int abuf_rows) { return 1024 + (size_t)2 * CB * abuf_rows * 128 + kWBytes + 256; }
+};
+
+template <int N_OUT, int CB, int T, bool WRES>
+__global__ void __launch_bounds__(256, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
+               const __grid_constant__ CUtensorMap tmW, const ConvGeom g, const float* __restrict__ bias,
+               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ out_bf, float* __restrict__ out_f32,
+               int relu) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  const int abuf_bytes = g.abuf_rows * 128;                       // one 64-channel block of one buffer
+  uint8_t* sA = base;                                             // [2][CB][abuf_rows][128]
+  uint8_t* sW = base + (size_t)2 * CB * abuf_bytes;               // resident: [9*CB][N_OUT][128]; streamed: [stages][N_OUT][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + ConvSmem<N_OUT, CB, T, WRES>::kWBytes);
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* t_full = bars + 4;        // [2]
+  uint64_t* t_empty = bars + 6;       // [2]
+  uint64_t* w_full = bars + 8;        // [kNumWStages] (or [1] resident)
+  uint64_t* w_empty = bars + 8 + kNumWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kNumWStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmemCols = (2 * T * N_OUT <= 32) ? 32 : (2 * T * N_OUT <= 64) ? 64 : (2 * T * N_OUT <= 128) ? 128
+                            : (2 * T * N_OUT <= 256) ? 256 : 512;
+  static_assert(2 * T * N_OUT <= 512, "accumulators exceed TMEM");
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
+      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
+    }
+    for (int i = 0; i < kNumWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA128); prefetch_tmap(&tmAhh); prefetch_tmap(&tmW); }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_items = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x + i*gridDim.x
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      if (WRES) {
+        mbar_arrive_expect_tx(&w_full[0], 9 * CB * ConvSmem<N_OUT, CB, T, WRES>::kWBytesPerKb);
+        for (int kb = 0; kb < 9 * CB; ++kb)
+          tma_load_2d(sW + (size_t)kb * N_OUT * 128, &tmW, 0, kb * N_OUT, &w_full[0]);
+      }
+      auto load_item = [&](int it) {
+        const int b = it & 1;
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int q0 = item * T * 128;
+        mbar_wait(&a_empty[b], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&a_full[b], (uint32_t)(CB * abuf_bytes));
+        for (int cb = 0; cb < CB; ++cb) {
+          uint8_t* dst = sA + (size_t)(b * CB + cb) * abuf_bytes;
+          tma_load_2d(dst, &tmAhh, cb * 64, q0 - g.hh, &a_full[b]);
+          for (int t = 0; t < T; ++t)
+            tma_load_2d(dst + (size_t)(g.hh + t * 128) * 128, &tmA128, cb * 64, q0 + t * 128, &a_full[b]);
+          tma_load_2d(dst + (size_t)(g.hh + T * 128) * 128, &tmAhh, cb * 64, q0 + T * 128, &a_full[b]);
+        }
+      };
+      if (my_items > 0) load_item(0);
+      uint32_t wcount = 0;
+      for (int it = 0; it < my_items; ++it) {
+        if (it + 1 < my_items) load_item(it + 1);
+        if (!WRES) {
+          for (int kb = 0; kb < 9 * CB; ++kb, ++wcount) {
+            const int s = wcount % kNumWStages;
+            mbar_wait(&w_empty[s], ((wcount / kNumWStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&w_full[s], N_OUT * 128);
+            tma_load_2d(sW + (size_t)s * N_OUT * 128, &tmW, 0, kb * N_OUT, &w_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
+      const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
+      if (WRES) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
+      uint32_t wcount = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&a_full[b], ph);
+        mbar_wait(&t_empty[b], ph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 9 * CB; ++kb) {
+          const int tap = kb / CB, cb = kb - tap * CB;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          const int off = (ky - 1) * g.Wp + (kx - 1);
+          uint32_t w_addr;
+          int s = 0;
+          if (WRES) {
+            w_addr = w_addr0 + (uint32_t)kb * N_OUT * 128;
+          } else {
+            s = wcount % kNumWStages;
+            mbar_wait(&w_full[s], (wcount / kNumWStages) & 1);
+            tc_fence_after();
+            w_addr = w_addr0 + (uint32_t)s * N_OUT * 128;
+          }
+          const uint32_t a_cb = a_addr0 + (uint32_t)(b * CB + cb) * abuf_bytes;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const uint32_t a_tile = a_cb + (uint32_t)(g.hh + t * 128 + off) * 128;
+            const uint32_t d_tmem = tmem_base + (uint32_t)((b * T + t) * N_OUT);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, make_smem_desc(a_tile + k * 32, 16, 1024, 0), make_smem_desc(w_addr + k * 32, 16, 1024, 0), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (!WRES) { umma_commit(&w_empty[s]); ++wcount; }
+        }
+        umma_commit(&t_full[b]);     // accumulators of this item complete -> epilogue
+        umma_commit(&a_empty[b]);    // smem rows of this item no longer read -> producer
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue =====================================
+    const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
+    const int HpWp = g.Hp * g.Wp;
+    for (int it = 0; it < my_items; ++it) {
+      const int b = it & 1;
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      mbar_wait(&t_full[b], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const int q = (item * T + t) * 128 + ew * 32 + lane;
+        const int n = q / HpWp, rem = q - n * HpWp;
+        const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
+        const bool valid = q < g.Q && xp >= 1 && xp <= g.W && yp >= 1 && yp <= g.H;
+        const size_t o_pad = (size_t)q * N_OUT;
+        const size_t o_f32 = (((size_t)n * g.H + (yp - 1)) * g.W + (xp - 1)) * N_OUT;
+#pragma unroll 1
+        for (int c = 0; c < N_OUT / 32; ++c) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
+          if (valid) {
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (mask_src) {
+              const uint4* mp = reinterpret_cast<const uint4*>(mask_src + o_pad + c * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint4 m = __ldg(mp + j4);
+                const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                  const uint32_t lo = mw[h] & 0xFFFFu, hi = mw[h] >> 16;
+                  if (!(lo != 0 && !(lo & 0x8000u))) v[j4 * 8 + h * 2] = 0.f;
+                  if (!(hi != 0 && !(hi & 0x8000u))) v[j4 * 8 + h * 2 + 1] = 0.f;
+                }
+              }
+            }
+            if (out_bf) {
+              uint4* op = reinterpret_cast<uint4*>(out_bf + o_pad + c * 32);
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                op[j4] = pk;
+              }
+            }
+            if (out_f32) {
+              float4* fp = reinterpret_cast<float4*>(out_f32 + o_f32 + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) fp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&t_empty[b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace tc
+}  // namespace udh

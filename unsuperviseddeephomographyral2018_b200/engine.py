@@ -55,6 +55,8 @@ class HomographyEngine(object):
         if self.ws_bytes == 0:
             raise _lib.UdhError("unsupported batch / patch size (%d, %d)" % (self.B, self.Pz))
         self.ws = torch.empty(self.ws_bytes, device=self.device, dtype=torch.uint8)
+        check(lib.udh_cnn_workspace_init(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, ops._stream()),
+              "udh_cnn_workspace_init")
         self.global_step = 0
         self.pg = process_group
         self.world_size = world_size
