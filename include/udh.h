@@ -163,6 +163,10 @@ int udh_debug_umma_probe(const void* A, int a_rows, const void* B, int b_rows, f
 size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout);
 int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W,
                       int cin, int cout, int relu, int dgrad, void* stream);
+/* tensor-core weight gradient of one layer: x [B,H,W,cin], g [B,H,W,cout] fp32 -> dW HWIO, db (both accumulated);
+ * scratch sized by udh_debug_tc_conv_scratch_bytes. */
+int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, float* db, void* scratch, int B, int H, int W, int cin,
+                       int cout, void* stream);
 
 #ifdef __cplusplus
 }

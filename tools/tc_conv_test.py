@@ -43,3 +43,25 @@ for c in cases:
     except Exception as e:
         print("case", c, "FAILED:", repr(e)[:300], flush=True)
         break
+
+def run_wgrad(B, H, cin, cout, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, H, H, cin, device="cuda", generator=g).bfloat16().float().contiguous()
+    go = (torch.randn(B, H, H, cout, device="cuda", generator=g) * 0.1).bfloat16().float().contiguous()
+    dW = torch.zeros(3, 3, cin, cout, device="cuda"); db = torch.zeros(cout, device="cuda")
+    nb = lib.udh_debug_tc_conv_scratch_bytes(B, H, H, cin, cout)
+    scratch = torch.empty(nb, device="cuda", dtype=torch.uint8)
+    rc = lib.udh_debug_tc_wgrad(P(x), P(go), P(dW), P(db), P(scratch), B, H, H, cin, cout, None)
+    assert rc == 0, lib.udh_last_error()
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (cout, cin, 3, 3), go.permute(0, 3, 1, 2), padding=1).permute(2, 3, 1, 0)
+    refb = go.sum(dim=(0, 1, 2))
+    e = (dW - ref).abs().max().item(); eb = (db - refb).abs().max().item()
+    print("wgrad B=%d H=%3d %3d->%3d  max|err dW|=%.3e (ref max %.2f)  max|err db|=%.3e (ref max %.2f)" % (B, H, cin, cout, e, ref.abs().max().item(), eb, refb.abs().max().item()), flush=True)
+
+for c in [(2, 128, 64, 64), (3, 64, 64, 64), (2, 32, 64, 128), (2, 32, 128, 128), (5, 16, 128, 128)]:
+    try:
+        run_wgrad(*c)
+    except Exception as e:
+        print("wgrad case", c, "FAILED:", repr(e)[:300], flush=True)
+        break

@@ -5,6 +5,7 @@
 
 #include "cnn_kernels.cuh"
 #include "conv_tc_kernels.cuh"
+#include "wgrad_tc_kernels.cuh"
 
 namespace udh {
 
@@ -245,6 +246,85 @@ int pool_bwd_bf16(const __nv_bfloat16* in, const __nv_bfloat16* gout, __nv_bfloa
   return check_launch("pool_bwd_bf16");
 }
 
+// db[c] += sum over all positions of a padded bf16 stream [Q][C] (borders are zero).  C in {64,128}.
+// thread = 8 channels (one 16-byte load) of one position per iteration; block-level reduction, then atomics.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ gsrc, float* __restrict__ db, int Q, int C) {
+  __shared__ float red[256][9];
+  const int lanes = C >> 3;                       // threads per position
+  const int ppb = 256 / lanes;                    // positions per block iteration
+  const int sub = threadIdx.x % lanes, prow = threadIdx.x / lanes;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int q = blockIdx.x * ppb + prow; q < Q; q += gridDim.x * ppb) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(gsrc + (size_t)q * C + sub * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < lanes) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+      for (int r = 0; r < ppb; ++r) s += red[r * lanes + threadIdx.x][j];
+      atomicAdd(db + threadIdx.x * 8 + j, s);
+    }
+  }
+}
+
+template <int N_OUT, int CBX, int T>
+int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float* db, int B, int H, int W, cudaStream_t st) {
+  tc::WgradGeom g;
+  g.Wp = W + 2;
+  g.Q = B * (H + 2) * (W + 2);
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  const int tiles = (g.Q + 127) / 128;
+  g.num_items = (tiles + T - 1) / T;
+  g.xrows = T * 128 + 2 * g.hh;
+  g.num_groups = CBX == 1 ? 5 : 9;
+  g.groups_per_y = 512 / N_OUT < g.num_groups ? (CBX == 1 ? 3 : 3) : g.num_groups;     // accumulators of one slice fit TMEM
+  if (g.groups_per_y * N_OUT > 512) g.groups_per_y = 512 / N_OUT;
+  const int gy = (g.num_groups + g.groups_per_y - 1) / g.groups_per_y;
+  constexpr int CBO = N_OUT / 64;
+  const int Cin = CBX * 64;
+  CUtensorMap tmX128, tmXhh, tmG;
+  uint64_t dimsX[2] = {(uint64_t)Cin, (uint64_t)g.Q}, strX[2] = {2, (uint64_t)Cin * 2};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh};
+  TRY(tc::make_tmap_bf16(&tmX128, x, 2, dimsX, strX, box128));
+  TRY(tc::make_tmap_bf16(&tmXhh, x, 2, dimsX, strX, boxhh));
+  uint64_t dimsG[2] = {(uint64_t)N_OUT, (uint64_t)g.Q}, strG[2] = {2, (uint64_t)N_OUT * 2};
+  TRY(tc::make_tmap_bf16(&tmG, gsrc, 2, dimsG, strG, box128));
+  const size_t stage = (size_t)CBX * g.xrows * 128 + (size_t)CBO * T * 16384;
+  const size_t smem = 1024 + 2 * stage + (CBX == 1 ? 16384 : 0) + 256;
+  UDH_REQUIRE(smem <= 232448, "tc wgrad: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+  auto kern = tc::tc_wgrad_kernel<N_OUT, CBX, T>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int gx = sms / gy;
+  if (gx > g.num_items) gx = g.num_items;
+  if (gx < 1) gx = 1;
+  kern<<<dim3(gx, gy), 256, smem, st>>>(tmX128, tmXhh, tmG, g, dW, CBX == 1 ? db : nullptr);
+  TRY(check_launch("tc_wgrad_kernel"));
+  if (CBX == 2 && db) {
+    colsum_bf16_kernel<<<296, 256, 0, st>>>(gsrc, db, g.Q, N_OUT);
+    TRY(check_launch("colsum_bf16"));
+  }
+  return UDH_OK;
+}
+
+// dW (HWIO fp32) += X^T-shifted . G ; db += sum G   for one layer, on padded bf16 streams
+int tc_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float* db, int B, int H, int W, int cin, int cout,
+             cudaStream_t st) {
+  if (cin == 64 && cout == 64) return launch_wgrad<64, 1, 2>(x, gsrc, dW, db, B, H, W, st);
+  if (cin == 64 && cout == 128) return launch_wgrad<128, 1, 1>(x, gsrc, dW, db, B, H, W, st);
+  if (cin == 128 && cout == 128) return launch_wgrad<128, 2, 1>(x, gsrc, dW, db, B, H, W, st);
+  set_error("tc_wgrad: unsupported channel combination %d -> %d", cin, cout);
+  return UDH_ENOSUP;
+}
+
 // input tensor index (into P / G) of conv layer i (i >= 1)
 inline int input_of(int i) { return (i == 2 || i == 4 || i == 6) ? 8 + (i - 2) / 2 : i - 1; }
 
@@ -308,14 +388,13 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     const int s = P / kConv[i].div;
     const int cin = kConv[i].cin, cout = kConv[i].cout;
     {
-      // weight gradient: interim path — fp32 CUDA-core wgrad on unpadded fp32 copies of the bf16 streams
       ProfScope ps(PROF_CONV_WGRAD0 + i, st);
-      TRY(unpad_cast(Gb(i), gA, B, s, s, cout, st));
       if (i == 0) {
+        // conv1_1 (Cin = 2): fp32 CUDA-core wgrad on an unpadded fp32 copy of its gradient stream
+        TRY(unpad_cast(Gb(0), gA, B, s, s, cout, st));
         TRY(wgrad3x3_simt(I1, I2, gA, grads + poff[0], grads + poff[1], B, s, s, cin, cout, st));
       } else {
-        TRY(unpad_cast(Pb(input_of(i)), gB, B, s, s, cin, st));
-        TRY(wgrad3x3_simt(gB, nullptr, gA, grads + poff[2 * i], grads + poff[2 * i + 1], B, s, s, cin, cout, st));
+        TRY(tc_wgrad(Pb(input_of(i)), Gb(i), grads + poff[2 * i], grads + poff[2 * i + 1], B, s, s, cin, cout, st));
       }
     }
     if (i == 0) break;
@@ -356,7 +435,25 @@ int tc_debug_conv(const float* x, const float* w, const float* bias, float* out,
   return UDH_OK;
 }
 
+// Debug / test entry: tensor-core weight gradient on fp32 NHWC tensors x [B,H,W,cin], g [B,H,W,cout] -> dW HWIO, db (accumulated).
+int tc_debug_wgrad(const float* x, const float* gsrc, float* dW, float* db, void* scratch, int B, int H, int W, int cin, int cout,
+                   cudaStream_t st) {
+  char* s = reinterpret_cast<char*>(scratch);
+  __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(s);
+  __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(s + al256((size_t)B * (H + 2) * (W + 2) * cin * 2));
+  UDH_CUDA(cudaMemsetAsync(scratch, 0, tc_debug_scratch_bytes(B, H, W, cin, cout), st));
+  TRY(pad_cast(x, xp, B, H, W, cin, st));
+  TRY(pad_cast(gsrc, gp, B, H, W, cout, st));
+  return tc_wgrad(xp, gp, dW, db, B, H, W, cin, cout, st);
+}
+
 }  // namespace udh
+
+extern "C" int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, float* db, void* scratch, int B, int H, int W, int cin,
+                                  int cout, void* stream) {
+  UDH_REQUIRE(x && g && dW && scratch, "udh_debug_tc_wgrad: null pointer");
+  return udh::tc_debug_wgrad(x, g, dW, db, scratch, B, H, W, cin, cout, udh::as_stream(stream));
+}
 
 extern "C" size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout) {
   return udh::tc_debug_scratch_bytes(B, H, W, cin, cout);
