@@ -174,8 +174,12 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
   // fc1 + ReLU + dropout (:126-129): split-K SGEMM into a zeroed accumulator, then the fused epilogue
   ProfScope ps_fc(PROF_FC_FWD, st);
   UDH_CUDA(cudaMemsetAsync(at<float>(ws, L.fc1_acc), 0, (size_t)B * 1024 * 4, st));
-  TRY(sgemm_simt(feat_in, feat, 1, params + PL.off[16], 1024, 1, at<float>(ws, L.fc1_acc), 1024, B, 1024, feat,
-                 B <= 256 ? 16 : 4, 0, st));
+  if (numeric_mode == UDH_NUMERIC_BF16) {
+    TRY(tc_fc1_fwd(feat_in, params + PL.off[16], at<float>(ws, L.fc1_acc), ws, L.tc, B, P, st));
+  } else {
+    TRY(sgemm_simt(feat_in, feat, 1, params + PL.off[16], 1024, 1, at<float>(ws, L.fc1_acc), 1024, B, 1024, feat,
+                   B <= 256 ? 16 : 4, 0, st));
+  }
   TRY(bias_act_dropout(at<float>(ws, L.fc1_acc), params + PL.off[17], at<float>(ws, L.act[11]), at<float>(ws, L.fc1d),
                        train ? at<uint8_t>(ws, L.mask2) : nullptr, B, 1024, 1, 1, seed, 2, st));
   // fc2, linear (:130-131)
@@ -207,9 +211,13 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
   TRY(sgemm_simt(dh4p, 8, 1, params + PL.off[18], 1, 8, dfc1, 1024, B, 1024, 8, 1, 0, st));          // dfc1d = dh4p . W2^T
   TRY(drop_relu_bwd(dfc1, train ? at<uint8_t>(ws, L.mask2) : nullptr, at<float>(ws, L.act[11]), (size_t)B * 1024, st));
   // fc1
-  TRY(sgemm_simt(feat_in, 1, feat, dfc1, 1024, 1, grads + PL.off[16], 1024, feat, 1024, B, 1, 1, st));  // dW1 += x^T . dfc1
+  if (numeric_mode == UDH_NUMERIC_BF16) {
+    TRY(tc_fc1_bwd(dfc1, grads + PL.off[16], gA, ws, L.tc, B, P, st));
+  } else {
+    TRY(sgemm_simt(feat_in, 1, feat, dfc1, 1024, 1, grads + PL.off[16], 1024, feat, 1024, B, 1, 1, st));  // dW1 += x^T . dfc1
+    TRY(sgemm_simt(dfc1, 1024, 1, params + PL.off[16], 1, 1024, gA, feat, B, feat, 1024, 1, 0, st));   // dx = dfc1 . W1^T
+  }
   TRY(colsum_accum(dfc1, grads + PL.off[17], B, 1024, st));
-  TRY(sgemm_simt(dfc1, 1024, 1, params + PL.off[16], 1, 1024, gA, feat, B, feat, 1024, 1, 0, st));   // dx = dfc1 . W1^T
   TRY(drop_relu_bwd(gA, train ? at<uint8_t>(ws, L.mask1) : nullptr, at<float>(ws, L.act[7]), (size_t)B * feat, st));
   prof_end(PROF_FC_BWD, st);
 

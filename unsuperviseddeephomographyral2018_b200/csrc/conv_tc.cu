@@ -6,6 +6,7 @@
 #include "cnn_kernels.cuh"
 #include "conv_tc_kernels.cuh"
 #include "wgrad_tc_kernels.cuh"
+#include "gemm_tc_kernels.cuh"
 
 namespace udh {
 
@@ -23,6 +24,7 @@ struct TcLayout {
   size_t G[11];      // padded bf16 gradients w.r.t. the same tensors (pre-activation for convs)
   size_t numel[11];  // padded element counts
   size_t wf[8], wd[8];   // packed bf16 weights, forward / dgrad (rotated)
+  size_t fc_x, fc_w, fc_dy;   // bf16 copies for the fc1 GEMMs: x [B,F], W [F,1024], dy [B,1024]
   size_t total;
   TcLayout(int B, int P_) {
     size_t o = 0;
@@ -37,6 +39,10 @@ struct TcLayout {
     for (int i = 0; i < 11; ++i) P[i] = take(numel[i] * 2);
     for (int i = 0; i < 11; ++i) G[i] = take(numel[i] * 2);
     for (int i = 0; i < 8; ++i) { wf[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); wd[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); }
+    const size_t feat = (size_t)(P_ / 8) * (P_ / 8) * 128;
+    fc_x = take((size_t)B * feat * 2);
+    fc_w = take(feat * 1024 * 2);
+    fc_dy = take((size_t)B * 1024 * 2);
     total = o;
   }
 };
@@ -325,6 +331,48 @@ int tc_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float
   return UDH_ENOSUP;
 }
 
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = pk;
+  }
+}
+int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
+  cast_bf16_kernel<<<grid1d((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(src, dst, n / 4);
+  return check_launch("cast_bf16");
+}
+
+// C[M][N] (+)= A . B on tensor cores.  a_inner/a_outer: dims of A's tensor (innermost first); same for B.
+template <bool A_MN, bool B_MN, bool ATOMIC>
+int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, const __nv_bfloat16* Bm, uint64_t b_inner, uint64_t b_outer,
+                float* C, int64_t ldc, int M, int N, int K, int k_splits, cudaStream_t st) {
+  tc::GemmGeom g;
+  g.M = M; g.N = N; g.ldc = ldc;
+  g.m_tiles = (M + 127) / 128; g.n_tiles = (N + 255) / 256;
+  const int kb = (K + 63) / 64;
+  g.k_splits = k_splits;
+  g.kb_per_split = (kb + k_splits - 1) / k_splits;
+  UDH_REQUIRE(g.kb_per_split * k_splits == kb, "tc gemm: k-blocks (%d) must divide evenly into %d splits", kb, k_splits);
+  CUtensorMap tmA, tmB;
+  uint64_t dA[2] = {a_inner, a_outer}, sA[2] = {2, a_inner * 2};
+  uint32_t boxA[2] = {64, A_MN ? 64u : 128u};
+  TRY(tc::make_tmap_bf16(&tmA, A, 2, dA, sA, boxA));
+  uint64_t dB[2] = {b_inner, b_outer}, sB[2] = {2, b_inner * 2};
+  uint32_t boxB[2] = {64, B_MN ? 64u : 256u};
+  TRY(tc::make_tmap_bf16(&tmB, Bm, 2, dB, sB, boxB));
+  const size_t smem = 1024 + (size_t)tc::kGemmStages * tc::kGemmStageBytes + 256;
+  auto kern = tc::tc_gemm_kernel<A_MN, B_MN, ATOMIC>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
+  kern<<<tiles < sms ? tiles : sms, 256, smem, st>>>(tmA, tmB, g, C);
+  return check_launch("tc_gemm_kernel");
+}
+
 // input tensor index (into P / G) of conv layer i (i >= 1)
 inline int input_of(int i) { return (i == 2 || i == 4 || i == 6) ? 8 + (i - 2) / 2 : i - 1; }
 
@@ -412,6 +460,35 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     }
   }
   return UDH_OK;
+}
+
+// fc1 forward on tensor cores: acc[B,1024] (zeroed by the caller) += x[B,F] . W[F,1024]
+int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, cudaStream_t st) {
+  TcLayout L(B, P);
+  char* tcw = at<char>(ws, tc_off);
+  const size_t feat = (size_t)(P / 8) * (P / 8) * 128;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_x);
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_w);
+  TRY(cast_bf16(x, xb, (size_t)B * feat, st));
+  TRY(cast_bf16(w, wb, feat * 1024, st));
+  const int kb = (int)(feat / 64);
+  int splits = 32;
+  while (kb % splits) splits >>= 1;
+  return launch_gemm<false, true, true>(xb, feat, (uint64_t)B, wb, 1024, feat, acc, 1024, B, 1024, (int)feat, splits, st);
+}
+
+// fc1 backward: dW[F,1024] = x^T . dy (stored: the gradient buffer is zero on entry), dx[B,F] = dy . W^T.
+// Uses the bf16 copies of x and W made by the forward of the same step.
+int tc_fc1_bwd(const float* dy, float* dW, float* dx, void* ws, size_t tc_off, int B, int P, cudaStream_t st) {
+  TcLayout L(B, P);
+  char* tcw = at<char>(ws, tc_off);
+  const size_t feat = (size_t)(P / 8) * (P / 8) * 128;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_x);
+  __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_w);
+  __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_dy);
+  TRY(cast_bf16(dy, dyb, (size_t)B * 1024, st));
+  TRY((launch_gemm<true, true, false>(xb, feat, (uint64_t)B, dyb, 1024, (uint64_t)B, dW, 1024, (int)feat, 1024, B, 1, st)));
+  return launch_gemm<false, false, false>(dyb, 1024, (uint64_t)B, wb, 1024, feat, dx, (int64_t)feat, B, (int)feat, 1024, 1, st);
 }
 
 // Debug / test entry: one tensor-core conv layer on fp32 NHWC tensors (pads + casts internally).
