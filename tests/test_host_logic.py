@@ -1,0 +1,86 @@
+"""CPU tests of the host side: CLI flags / path munging mirror the reference, on-disk list parsing, test-mode summary
+helpers, and the data-parallel contract (world_size-2 gloo): allreduce(sum) with 1/N folded into Adam == the reference's
+get_average_grads (utils/utils.py:380-403) followed by apply_gradients."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cli_flags_match_reference_defaults():
+    sys.path.insert(0, ROOT)
+    import homography_CNN_synthetic as cli
+    a = cli.build_parser().parse_args([])
+    # defaults of code/homography_CNN_synthetic.py:49-85
+    assert (a.mode, a.loss_type, a.num_gpus, a.batch_size, a.lr, a.min_lr) == ('train', 'l1_loss', 2, 128, 1e-4, .9e-4)
+    assert (a.img_w, a.img_h, a.patch_size, a.do_augment, a.augment_list) == (320, 240, 128, 0.5, ['normalize'])
+    assert a.use_batch_norm is False and a.resume is False and a.retrain is False and a.save_visual is True and a.visual is False
+    a = cli.build_parser().parse_args(['--mode', 'test', '--loss_type', 'h_loss', '--data_path', '/d/', '--resume', 'True'])
+    a = cli.resolve_paths(a)
+    assert a.pts1_file == '/d/pts1.txt' and a.test_gt_file == '/d/test_gt.txt' and a.filenames_file == '/d/train_synthetic.txt'
+    assert a.model_dir.endswith('synthetic_models/h_loss_normalize')
+    assert a.log_dir.endswith('h_loss_normalizetest/h_loss_normalize/h_loss_normalizetest/')     # suffix applied twice (:94-100)
+    assert a.resume is True
+    with pytest.raises(SystemExit):
+        cli.build_parser().parse_args(['--loss_type', 'nope'])
+    assert cli.find_percentile([1, 2, 3, 4, 5, 6, 7, 8, 9, 10]) == [2.0, 5.0, 8.5]
+
+
+def test_on_disk_list_parsing(tmp_path):
+    from unsuperviseddeephomographyral2018_b200 import dataloader as dl
+    (tmp_path / "list.txt").write_text("a.jpg a.jpg\nb.jpg b.jpg\n")
+    np.savetxt(tmp_path / "pts1.txt", np.array([[50, 60, 178, 60, 178, 188, 50, 188], [45, 45, 173, 45, 173, 173, 45, 173]], dtype=float))
+    np.savetxt(tmp_path / "gt.txt", np.array([[1, -2, 3, -4, 5, -6, 7, -8], [0] * 8], dtype=float))
+    names, pts1, gt = dl.read_img_and_gt(str(tmp_path / "list.txt"), str(tmp_path / "pts1.txt"), str(tmp_path / "gt.txt"))
+    assert names == [["a.jpg", "a.jpg"], ["b.jpg", "b.jpg"]] and pts1.shape == (2, 8) and gt[0, 1] == -2
+    assert dl.count_text_lines(str(tmp_path / "list.txt")) == 2
+    names, pts1, gt = dl.read_img_and_gt(str(tmp_path / "list.txt"), str(tmp_path / "pts1.txt"), None)
+    assert gt is None
+    assert dl.dataloader_params._fields == ('data_path', 'filenames_file', 'pts1_file', 'gt_file', 'mode', 'batch_size', 'img_h',
+                                            'img_w', 'patch_size', 'augment_list', 'do_augment')
+
+
+def test_model_params_namedtuple_matches_reference():
+    from unsuperviseddeephomographyral2018_b200 import homography_model as hm
+    assert hm.homography_model_params._fields == ('mode', 'batch_size', 'patch_size', 'img_w', 'img_h', 'loss_type', 'use_batch_norm',
+                                                  'augment_list', 'leftright_consistent_weight')
+
+
+def test_data_parallel_contract_gloo_world2(tmp_path):
+    script = tmp_path / "dp.py"
+    script.write_text(textwrap.dedent('''
+        import os, sys
+        sys.path.insert(0, %r)
+        import torch, torch.distributed as dist
+        from oracle import oracle as O
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        torch.manual_seed(0)
+        p = torch.randn(1000); m = torch.zeros(1000); v = torch.zeros(1000)
+        tower = [torch.randn(1000, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)]
+        # reference: mean over towers, then Adam
+        ref_p, _, _ = O.adam_step(p, O.average_grads([[t] for t in tower])[0], m, v, 1, 1e-3)
+        # ours: every rank holds its own gradient, allreduce(sum), 1/N folded into the update (grad_scale)
+        g = tower[rank].clone()
+        dist.all_reduce(g)
+        mine, _, _ = O.adam_step(p, g * (1.0 / world), m, v, 1, 1e-3)
+        assert torch.allclose(mine, ref_p, atol=1e-7), (mine - ref_p).abs().max()
+        # replicated update: all ranks end with identical parameters
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        assert all(torch.equal(gathered[0], x) for x in gathered)
+        # per-rank batch sharding as tf.split(batch, num_gpus) (homography_CNN_synthetic.py:199-207)
+        full = torch.arange(8)
+        assert torch.equal(full.chunk(world)[rank], full[rank * 4:(rank + 1) * 4])
+        dist.destroy_process_group()
+        print("rank", rank, "ok")
+    ''' % ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
