@@ -98,12 +98,24 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
+def host_threads():
+    """All the host threads this process may actually use: min(affinity, cgroup cpu quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_pairs_per_s(sample_b, steps, warmup, loss_type):
     """The restated reference (oracle/, PyTorch-CPU fp32, all host threads) on a bounded sample of the workload."""
     import torch
     from oracle import oracle as O
     from unsuperviseddeephomographyral2018_b200 import params as P
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     specs = P.param_specs()
     flat = torch.tensor(P.init_flat(0))
     m, v = torch.zeros_like(flat), torch.zeros_like(flat)
@@ -224,28 +236,52 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    # ---- roofline of the dominant kernel (by measured share of the step) ----
+    # ---- roofline of the dominant kernel family (by measured share of the step) ----
+    layers = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv4_1", "conv4_2"]
+    fam = {}          # family -> [ms total, launches, algorithmic flops, algorithmic bytes]
+
+    def add(f, ms, n, flops=0.0, byts=0.0):
+        e = fam.setdefault(f, [0.0, 0, 0.0, 0.0]); e[0] += ms; e[1] += n; e[2] += flops; e[3] += byts
+    tc = numeric == "bf16"
+    for name, (tms, cnt) in phases.items():
+        head, _, kind = name.partition(".")
+        if head in layers:
+            li = layers.index(head)
+            flops = 2.0 * CONV_MACS[li] * B * cnt
+            if li == 0 or not tc:
+                add("conv3x3 fp32 CUDA-core kernels" if not tc else "conv1_1 CUDA-core kernels", tms, cnt, flops)
+            elif kind == "wgrad":
+                add("tc_wgrad_kernel (tcgen05 weight gradient, conv1_2..conv4_2)", tms, cnt, flops)
+            else:
+                add("tc_conv_kernel (tcgen05 implicit-GEMM conv fwd+dgrad, conv1_2..conv4_2)", tms, cnt, flops)
+        elif name == "adam":
+            add("adam_kernel", tms, cnt, 0.0, 28.0 * 34192264 * cnt)
+        elif name.startswith("fc"):
+            add("fc1/fc2 GEMMs", tms, cnt, 2.0 * 33.56e6 * B * cnt * (1 if name == "fc.fwd" else 2))
+        else:
+            add(name, tms, cnt)
     roof = None
-    if phases:
-        top = max(phases.items(), key=lambda kv: kv[1][0])
-        name, (tms, cnt) = top
-        per_launch_ms = tms / cnt
-        if name.startswith("conv"):
-            layer = ["conv1_1", "conv1_2", "conv2_1", "conv2_2", "conv3_1", "conv3_2", "conv4_1", "conv4_2"].index(name.split(".")[0])
-            flops = 2.0 * CONV_MACS[layer] * B
-            ach = flops / (per_launch_ms * 1e-3) / 1e12
+    if fam:
+        name, (tms, cnt, flops, byts) = max(fam.items(), key=lambda kv: kv[1][0])
+        share = tms / K / ms_step
+        if flops:
+            ach = flops / (tms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peaks["source"] + ", sustained bf16", "ms_per_launch": per_launch_ms,
-                    "share_of_step": tms / K / ms_step}
-        elif name == "adam":
-            byts = 28.0 * 34192264
-            ach = byts / (per_launch_ms * 1e-3) / 1e9
-            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                    "traffic": None, "peak_source": peaks["source"], "ms_per_launch": per_launch_ms, "share_of_step": tms / K / ms_step}
+                    "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                    "launches_per_step": cnt / K, "ms_per_step": tms / K, "share_of_step": share,
+                    "algorithmic_work": "2*MAC(layer)*B per launch, MACs from SURVEY 8a row C"}
         else:
-            roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
-                    "ms_per_launch": per_launch_ms, "share_of_step": tms / K / ms_step}
+            ach = byts / (tms * 1e-3) / 1e9 if byts else None
+            roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"] if ach else None, "traffic": None, "peak_source": peaks["source"],
+                    "launches_per_step": cnt / K, "ms_per_step": tms / K, "share_of_step": share}
+        tr = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if roof and os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(name.split(" ")[0])
+            except Exception:
+                pass
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sb = 8

@@ -403,7 +403,7 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
   {
     // conv1_1 (K = 18): fp32 CUDA-core kernel writing the padded bf16 stream directly
     ProfScope ps(PROF_CONV_FWD0, st);
-    TRY(conv3x3_simt_bf16out(I1, I2, params + poff[0], params + poff[1], Pb(0), B, P, P, 2, 64, 1, st));
+    TRY(conv1_fwd_bf16(I1, I2, params + poff[0], params + poff[1], Pb(0), B, P, P, st));
   }
   for (int i = 1; i < 8; ++i) {
     const int s = P / kConv[i].div;
@@ -438,9 +438,8 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     {
       ProfScope ps(PROF_CONV_WGRAD0 + i, st);
       if (i == 0) {
-        // conv1_1 (Cin = 2): fp32 CUDA-core wgrad on an unpadded fp32 copy of its gradient stream
-        TRY(unpad_cast(Gb(0), gA, B, s, s, cout, st));
-        TRY(wgrad3x3_simt(I1, I2, gA, grads + poff[0], grads + poff[1], B, s, s, cin, cout, st));
+        // conv1_1 (Cin = 2): fp32 CUDA-core wgrad reading the bf16 gradient stream directly
+        TRY(conv1_wgrad_bf16(I1, I2, Gb(0), grads + poff[0], grads + poff[1], B, s, s, st));
       } else {
         TRY(tc_wgrad(Pb(input_of(i)), Gb(i), grads + poff[2 * i], grads + poff[2 * i + 1], B, s, s, cin, cout, st));
       }
