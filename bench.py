@@ -63,7 +63,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
@@ -183,11 +183,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled (nvidia-smi, 100 ms) from the warm-up to the end of the e2e loop: the timed region itself can be
+    # shorter than one sampling period
+    sampler = ClockSampler(local); sampler.start()
     for i in range(W):
         eng.train_step(batches[i % nb])
     barrier()
     _lib.lib.udh_prof_enable(1); _lib.lib.udh_prof_reset()
-    sampler = ClockSampler(local); sampler.start()
     launches0 = _lib.lib.udh_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -195,7 +197,6 @@ def run_ours(args):
         eng.train_step(batches[i % nb])
     e1.record()
     barrier()
-    clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.lib.udh_launch_count() - launches0
     phases = _lib.prof_read_all()
@@ -229,8 +230,26 @@ def run_ours(args):
         ms_e = float(t[0].item())
         e2e = {"value": B * world * K / (ms_e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": stepper.h2d_bytes * world,
                "d2h_bytes_per_step": stepper.d2h_bytes * world, "ms_per_step": ms_e / K, "wall_ms_per_step": float(t[1].item()) / K,
-               "api": "trainer.HostStepper.step(pinned post-dataloader tensors)", "last_h_loss": last["h_loss"] if last else None}
+               "api": "trainer.HostStepper.step(pinned post-dataloader fp32 tensors, the reference's feed)", "last_h_loss": last["h_loss"] if last else None}
+        # variant: the host hands over the decoded uint8 images; normalise / gray / patch gather run on the device
+        host8 = [trainer.pin_batch_u8(b["I_u8"], b["I_prime_u8"], b["pts1"], b["gt"]) for b in batches]
+        for i in range(3):
+            stepper.step_u8(host8[i % nb])
+        stepper.flush(); barrier()
+        e0.record()
+        for i in range(K):
+            stepper.step_u8(host8[i % nb])
+        last8 = stepper.flush()
+        e1.record(); barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["uint8_input_variant"] = {"value": B * world * K / (float(t.item()) * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": stepper.h2d_bytes * world,
+                                      "d2h_bytes_per_step": stepper.d2h_bytes * world, "ms_per_step": float(t.item()) / K,
+                                      "api": "trainer.HostStepper.step_u8(pinned decoded uint8 images; device-side normalise/gray/crop)",
+                                      "last_h_loss": last8["h_loss"] if last8 else None}
 
+    clocks = sampler.stop()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -125,6 +125,14 @@ int udh_cnn_fwd(const float* params, const float* I1, const float* I2, float* h4
 /* dh4p[B,8] -> grads (ACCUMULATED into the flat buffer: caller zeroes it once per step). */
 int udh_cnn_bwd(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
                 size_t ws_bytes, int B, int P, int train, int numeric_mode, void* stream);
+/* The same backward in two halves, so the caller can start the allreduce of the fully connected gradients (98 % of the
+ * bytes: fc1 is 33.5 M of the 34.2 M parameters) while the convolution backward is still running:
+ * UDH_BWD_HEAD = fc2 + fc1 (leaves d(conv4_2 pre-activation) in the workspace), UDH_BWD_CONVS = the conv stack. */
+#define UDH_BWD_ALL 0
+#define UDH_BWD_HEAD 1
+#define UDH_BWD_CONVS 2
+int udh_cnn_bwd_phase(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
+                      size_t ws_bytes, int B, int P, int train, int numeric_mode, int phase, void* stream);
 /* device pointers (inside ws) of the uint8 keep-masks of the last train-mode forward: [B,(P/8)^2*128] and [B,1024]. */
 int udh_cnn_dropout_masks(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, const uint8_t** mask_conv4,
                           const uint8_t** mask_fc1);
@@ -142,6 +150,13 @@ size_t udh_param_total_floats(int P);
  * computed by the caller (t is 1-based).  If zero_grad != 0 the gradient buffer is cleared in the same pass. */
 int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                   float eps, float grad_scale, int zero_grad, void* stream);
+
+/* ---- device-side input pipeline (dataloader.py:99-100,172-177,203-227) ------------------------
+ * I, I_prime: uint8 [B,img_h,img_w,3] decoded images; pts1 [B,8].  Writes the post-dataloader tensors the step
+ * consumes: I_aug fp32 [B,img_h,img_w,3] (normalised with I's statistics), gray patches I1, I2 fp32 [B,P,P] at
+ * (x0,y0) = pts1[0:2], and patch_origin[B] = y0*img_w + x0 (the first patch index of each sample). */
+int udh_prep_inputs_u8(const uint8_t* I, const uint8_t* I_prime, const float* pts1, float* I_aug, float* I1, float* I2,
+                       int32_t* patch_origin, int B, int img_h, int img_w, int P, void* stream);
 
 /* ---- instrumentation read by bench.py -------------------------------------------------------------------------
  * udh_launch_count: kernels this library has launched in this process (monotonic).

@@ -327,3 +327,41 @@ def test_full_size_properties_B128(udh):
     for k in ("l1_loss", "rec_loss", "ssim_loss", "l1_smooth_loss", "h_loss", "bounded_h_loss"):
         assert abs(d4[k] - d128[k]) <= 1e-5 * max(1.0, abs(d4[k])), k
     assert d128["num_fail"] == d4["num_fail"] * (B // 4)
+
+
+# ------------------------------------------------------------------------------------------------ device-side inputs
+def test_device_input_pipeline_and_synthetic_generator(udh):
+    """udh_prep_inputs_u8 (normalise / gray / patch gather from uint8) == the oracle's post-dataloader tensors, and the
+    on-device synthetic generator produces self-consistent pairs (warp with H_gt reproduces I2)."""
+    import ctypes
+    from unsuperviseddeephomographyral2018_b200 import synthetic, trainer
+    batch = O.make_batch(12, 3)
+    I_u8 = torch.tensor(batch["I_u8"]).cuda(); Ip_u8 = torch.tensor(batch["I_prime_u8"]).cuda()
+    pts1 = batch["pts1"].cuda().contiguous()
+    I_aug = torch.empty(3, 240, 320, 3, device="cuda"); I1 = torch.empty(3, 128, 128, device="cuda"); I2 = torch.empty_like(I1)
+    origin = torch.empty(3, device="cuda", dtype=torch.int32)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert udh.lib.lib.udh_prep_inputs_u8(p(I_u8), p(Ip_u8), p(pts1), p(I_aug), p(I1), p(I2), p(origin), 3, 240, 320, 128, None) == 0
+    torch.cuda.synchronize()
+    assert (I_aug.cpu() - batch["I_aug"]).abs().max() < 1e-6
+    assert (I1.cpu() - batch["I1_aug"][..., 0]).abs().max() < 1e-6 and (I2.cpu() - batch["I2_aug"][..., 0]).abs().max() < 1e-6
+    assert torch.equal(origin.cpu(), batch["patch_indices"][:, 0])
+    # on-device generator: same distribution rules, self-consistent pair
+    sb = synthetic.make_batch(8, seed=3)
+    assert sb["pts1"][:, 0].min() >= 45 and sb["pts1"][:, 0].max() <= 147 and sb["pts1"][:, 1].min() >= 45 and sb["pts1"][:, 1].max() <= 67
+    assert sb["gt"].abs().max() <= 45 and torch.equal(sb["gt"], sb["gt"].round())
+    Hgt = udh.ops.dlt_forward(sb["pts1"], sb["gt"])
+    _, sums = udh.ops.warp_loss_forward(sb["I_aug"], Hgt, sb["I2_aug"], sb["patch_indices"], 128, 128, want_pred=False)
+    assert sums[0].item() / (8 * 128 * 128) < 1.0 / 69.0
+    # host stepper, both input variants, agree with a direct engine step on the same data
+    eng = udh.engine.HomographyEngine(8, seed=0, loss_type="h_loss", lr=5e-4)
+    st = trainer.HostStepper(eng)
+    st.step(trainer.pin_batch(sb)); r_f32 = st.flush()
+    eng2 = udh.engine.HomographyEngine(8, seed=0, loss_type="h_loss", lr=5e-4)
+    st2 = trainer.HostStepper(eng2)
+    st2.step_u8(trainer.pin_batch_u8(sb["I_u8"], sb["I_prime_u8"], sb["pts1"], sb["gt"])); r_u8 = st2.flush()
+    eng3 = udh.engine.HomographyEngine(8, seed=0, loss_type="h_loss", lr=5e-4)
+    d = eng3.losses_dict(eng3.train_step(sb))
+    for k in ("h_loss", "l1_loss", "rec_loss"):
+        assert abs(r_f32[k] - d[k]) <= 1e-5 * max(1, abs(d[k])) and abs(r_u8[k] - d[k]) <= 1e-4 * max(1, abs(d[k])), k
+    assert st2.h2d_bytes < st.h2d_bytes / 2

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libudh.so")
 
 OK, EINVAL, ECUDA, ENOSUP, EWS = 0, -1, -2, -3, -4
 NUMERIC_FP32, NUMERIC_BF16 = 0, 1
+BWD_ALL, BWD_HEAD, BWD_CONVS = 0, 1, 2
 LOSS_L1, LOSS_REC, LOSS_L1_SMOOTH = 0, 1, 2
 NSUMS, NLOSSES, NMETRICS = 8, 8, 4
 L_REC, L_SSIM, L_L1, L_L1_SMOOTH, L_NCC = 0, 1, 2, 3, 4
@@ -37,6 +38,8 @@ SIGNATURES = {
                             c_void_p]),
     "udh_cnn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                             c_void_p]),
+    "udh_cnn_bwd_phase": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
+                                  c_int, c_void_p]),
     "udh_cnn_dropout_masks": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p)]),
     "udh_cnn_activation": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_size_t)]),
     "udh_param_offset": (c_int, [c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
@@ -48,6 +51,8 @@ SIGNATURES = {
     "udh_debug_tc_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p]),
     "udh_debug_tc_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "udh_prep_inputs_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p]),
     "udh_launch_count": (c_ulonglong, []),
     "udh_prof_enable": (c_int, [c_int]),
     "udh_prof_reset": (c_int, []),

@@ -190,7 +190,13 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
 
 extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
                            size_t ws_bytes, int B, int P, int train, int numeric_mode, void* stream) {
+  return udh_cnn_bwd_phase(params, I1, I2, dh4p, grads, ws, ws_bytes, B, P, train, numeric_mode, UDH_BWD_ALL, stream);
+}
+
+extern "C" int udh_cnn_bwd_phase(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
+                                 size_t ws_bytes, int B, int P, int train, int numeric_mode, int phase, void* stream) {
   TRY(check_cnn_args("udh_cnn_bwd", B, P, numeric_mode));
+  UDH_REQUIRE(phase == UDH_BWD_ALL || phase == UDH_BWD_HEAD || phase == UDH_BWD_CONVS, "udh_cnn_bwd_phase: bad phase %d", phase);
   UDH_REQUIRE(params && I1 && I2 && dh4p && grads && ws, "udh_cnn_bwd: null pointer");
   Workspace L(B, P, numeric_mode);
   if (ws_bytes < L.total) { set_error("udh_cnn_bwd: workspace too small (%zu < %zu)", ws_bytes, L.total); return UDH_EWS; }
@@ -204,6 +210,7 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
   const float* fc1d = at<float>(ws, L.fc1d);
   const float* feat_in = train ? at<float>(ws, L.a4d) : at<float>(ws, L.act[7]);
 
+  if (phase != UDH_BWD_CONVS) {
   // fc2
   prof_begin(PROF_FC_BWD, st);
   TRY(sgemm_simt(fc1d, 1, 1024, dh4p, 8, 1, grads + PL.off[18], 8, 1024, 8, B, 1, 1, st));          // dW2 += fc1d^T . dh4p
@@ -220,6 +227,8 @@ extern "C" int udh_cnn_bwd(const float* params, const float* I1, const float* I2
   TRY(colsum_accum(dfc1, grads + PL.off[17], B, 1024, st));
   TRY(drop_relu_bwd(gA, train ? at<uint8_t>(ws, L.mask1) : nullptr, at<float>(ws, L.act[7]), (size_t)B * feat, st));
   prof_end(PROF_FC_BWD, st);
+  }
+  if (phase == UDH_BWD_HEAD) return UDH_OK;
 
   if (numeric_mode == UDH_NUMERIC_BF16) {
     return tc_cnn_bwd_convs(params, PL.off, I1, I2, grads, gA, gB, ws, L.act, L.tc, B, P, st);

@@ -37,7 +37,7 @@ __device__ __forceinline__ void load_halo(float* in_s, const float* __restrict__
       in_s[c * PLANE + r * PITCH + cc] = v;
     }
   } else {
-    constexpr int Q = CK / 4;
+    constexpr int Q = CK >= 4 ? CK / 4 : 1;
     for (int it = threadIdx.x; it < NPIX * Q; it += blockDim.x) {
       const int p = it / Q, q = it - p * Q;
       const int r = p / (TW + 2), cc = p - r * (TW + 2);

@@ -236,7 +236,7 @@ int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, c
   pad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
   return check_launch("pad_cast");
 }
-int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
+[[maybe_unused]] int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * H * W * (C / 4);
   unpad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
   return check_launch("unpad_cast");

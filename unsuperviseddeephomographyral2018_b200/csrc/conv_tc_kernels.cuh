@@ -117,46 +117,52 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
-      const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
-      if (WRES) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
-      uint32_t wcount = 0;
-      for (int it = 0; it < my_items; ++it) {
-        const int b = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&a_full[b], ph);
-        mbar_wait(&t_empty[b], ph ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < 9 * CB; ++kb) {
-          const int tap = kb / CB, cb = kb - tap * CB;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const int off = (ky - 1) * g.Wp + (kx - 1);
-          uint32_t w_addr;
-          int s = 0;
-          if (WRES) {
-            w_addr = w_addr0 + (uint32_t)kb * N_OUT * 128;
-          } else {
-            s = wcount % kNumWStages;
-            mbar_wait(&w_full[s], (wcount / kNumWStages) & 1);
-            tc_fence_after();
-            w_addr = w_addr0 + (uint32_t)s * N_OUT * 128;
-          }
-          const uint32_t a_cb = a_addr0 + (uint32_t)(b * CB + cb) * abuf_bytes;
+    // The whole warp stays converged (so addresses and descriptors live in uniform registers); one elected lane issues.
+    constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
+    const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
+    if (WRES) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
+    uint32_t wcount = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int b = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&a_full[b], ph);
+      mbar_wait(&t_empty[b], ph ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < 9 * CB; ++kb) {
+        const int tap = kb / CB, cb = kb - tap * CB;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int off = (ky - 1) * g.Wp + (kx - 1);
+        uint32_t w_addr;
+        int s = 0;
+        if (WRES) {
+          w_addr = w_addr0 + (uint32_t)kb * N_OUT * 128;
+        } else {
+          s = wcount % kNumWStages;
+          mbar_wait(&w_full[s], (wcount / kNumWStages) & 1);
+          tc_fence_after();
+          w_addr = w_addr0 + (uint32_t)s * N_OUT * 128;
+        }
+        const uint32_t a_lo = desc_lo(a_addr0 + (uint32_t)(b * CB + cb) * abuf_bytes + (uint32_t)(g.hh + off) * 128, 16);
+        const uint32_t w_lo = desc_lo(w_addr, 16);
+        const uint32_t d0 = tmem_base + (uint32_t)(b * T * N_OUT);
+        if (elect_one()) {
 #pragma unroll
           for (int t = 0; t < T; ++t) {
-            const uint32_t a_tile = a_cb + (uint32_t)(g.hh + t * 128 + off) * 128;
-            const uint32_t d_tmem = tmem_base + (uint32_t)((b * T + t) * N_OUT);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, make_smem_desc(a_tile + k * 32, 16, 1024, 0), make_smem_desc(w_addr + k * 32, 16, 1024, 0), idesc,
+            for (int k = 0; k < 4; ++k)     // +1024 (16-byte units) per 128-row tile, +2 per 32-byte k-step
+              umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if (!WRES) { umma_commit(&w_empty[s]); ++wcount; }
+          if (!WRES) umma_commit(&w_empty[s]);
         }
+        __syncwarp();
+        if (!WRES) ++wcount;
+      }
+      if (elect_one()) {
         umma_commit(&t_full[b]);     // accumulators of this item complete -> epilogue
         umma_commit(&a_empty[b]);    // smem rows of this item no longer read -> producer
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================

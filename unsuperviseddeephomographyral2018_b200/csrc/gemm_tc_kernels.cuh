@@ -83,28 +83,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, 256, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      uint32_t cnt = 0;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int b = i & 1;
-        mbar_wait(&t_empty[b], ((i >> 1) & 1) ^ 1);
+    // whole warp converged; one elected lane issues
+    constexpr uint32_t idesc = make_idesc_bf16(128, 256, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    uint32_t cnt = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&t_empty[b], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < g.kb_per_split; ++kb, ++cnt) {
+        const int s = cnt % kGemmStages;
+        mbar_wait(&full[s], (cnt / kGemmStages) & 1);
         tc_fence_after();
-        for (int kb = 0; kb < g.kb_per_split; ++kb, ++cnt) {
-          const int s = cnt % kGemmStages;
-          mbar_wait(&full[s], (cnt / kGemmStages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(base + (size_t)s * kGemmStageBytes), b_addr = a_addr + 16384;
+        const uint32_t a_addr = smem_u32(base + (size_t)s * kGemmStageBytes), b_addr = a_addr + 16384;
+        const uint32_t a_lo = desc_lo(a_addr, A_MN ? 8192 : 16), b_lo = desc_lo(b_addr, B_MN ? 8192 : 16);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = A_MN ? make_smem_desc(a_addr + k * 2048, 8192, 1024, 0) : make_smem_desc(a_addr + k * 32, 16, 1024, 0);
-            const uint64_t bd = B_MN ? make_smem_desc(b_addr + k * 2048, 8192, 1024, 0) : make_smem_desc(b_addr + k * 32, 16, 1024, 0);
-            umma_bf16(tmem_base + (uint32_t)(b * 256), ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)(b * 256), desc_from_lo(a_lo + k * (A_MN ? 128 : 2)), desc_from_lo(b_lo + k * (B_MN ? 128 : 2)),
+                      idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
-        umma_commit(&t_full[b]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&t_full[b]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;

@@ -145,6 +145,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t start, uint32_t lbo_
   return d;
 }
 
+// Fast path for issue loops: the upper word is constant (SBO = 1024 B, version 1, SWIZZLE_128B, base_offset 0); the lower
+// word is (start >> 4) | (LBO >> 4) << 16, so stepping the start address is one 32-bit add.
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t start, uint32_t lbo_bytes) { return ((start & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | lo; }
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, dense.  a_mn / b_mn: 1 = MN-major operand.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |

@@ -88,49 +88,53 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 1, 1);
-      const uint32_t ones_addr = smem_u32(sOnes);
-      for (int it = 0; it < my_items; ++it) {
-        const int s = it & 1;
-        mbar_wait(&full[s], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t x_addr = smem_u32(sStage + (size_t)s * stage_bytes);
-        const uint32_t g_addr = x_addr + (uint32_t)(CBX * xblk_bytes);
+    // whole warp converged; one elected lane issues (see conv_tc_kernels.cuh)
+    constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 1, 1);
+    const uint32_t ones_addr = smem_u32(sOnes);
+    for (int it = 0; it < my_items; ++it) {
+      const int s = it & 1;
+      mbar_wait(&full[s], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t x_addr = smem_u32(sStage + (size_t)s * stage_bytes);
+      const uint32_t g_addr = x_addr + (uint32_t)(CBX * xblk_bytes);
 #pragma unroll 1
-        for (int t = 0; t < T; ++t) {
+      for (int t = 0; t < T; ++t) {
 #pragma unroll 1
-          for (int gl = 0; gl < g_count; ++gl) {
-            const int gi = g_begin + gl;
-            uint32_t a_start, lbo;
-            if (CBX == 1) {
-              const int tap0 = 2 * gi;
-              const int off0 = (tap0 / 3 - 1) * g.Wp + (tap0 % 3 - 1);
-              a_start = x_addr + (uint32_t)(g.hh + t * 128 + off0) * 128;
-              if (gi < 4) {
-                const int tap1 = tap0 + 1;
-                const int off1 = (tap1 / 3 - 1) * g.Wp + (tap1 % 3 - 1);
-                lbo = (uint32_t)(off1 - off0) * 128;
-              } else {
-                lbo = ones_addr - a_start;                      // second M block = the ones rows (bias gradient)
-              }
+        for (int gl = 0; gl < g_count; ++gl) {
+          const int gi = g_begin + gl;
+          uint32_t a_start, lbo;
+          if (CBX == 1) {
+            const int tap0 = 2 * gi;
+            const int off0 = (tap0 / 3 - 1) * g.Wp + (tap0 % 3 - 1);
+            a_start = x_addr + (uint32_t)(g.hh + t * 128 + off0) * 128;
+            if (gi < 4) {
+              const int tap1 = tap0 + 1;
+              const int off1 = (tap1 / 3 - 1) * g.Wp + (tap1 % 3 - 1);
+              lbo = (uint32_t)(off1 - off0) * 128;
             } else {
-              const int off = (gi / 3 - 1) * g.Wp + (gi % 3 - 1);
-              a_start = x_addr + (uint32_t)(g.hh + t * 128 + off) * 128;
-              lbo = (uint32_t)xblk_bytes;                       // second M block = channels 64..127
+              lbo = ones_addr - a_start;                      // second M block = the ones rows (bias gradient)
             }
-            const uint32_t b_start = g_addr + (uint32_t)t * 16384;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(gl * N_OUT);
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk)
-              umma_bf16(d_tmem, make_smem_desc(a_start + kk * 2048, lbo, 1024, 0),
-                        make_smem_desc(b_start + kk * 2048, (uint32_t)gblk_bytes, 1024, 0), idesc, (it > 0 || t > 0 || kk > 0) ? 1u : 0u);
+          } else {
+            const int off = (gi / 3 - 1) * g.Wp + (gi % 3 - 1);
+            a_start = x_addr + (uint32_t)(g.hh + t * 128 + off) * 128;
+            lbo = (uint32_t)xblk_bytes;                       // second M block = channels 64..127
           }
+          const uint32_t a_lo = desc_lo(a_start, lbo);
+          const uint32_t b_lo = desc_lo(g_addr + (uint32_t)t * 16384, (uint32_t)gblk_bytes);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(gl * N_OUT);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)                     // 16 positions = 2048 bytes = 128 sixteen-byte units per k-step
+              umma_bf16(d_tmem, desc_from_lo(a_lo + kk * 128), desc_from_lo(b_lo + kk * 128), idesc, (it > 0 || t > 0 || kk > 0) ? 1u : 0u);
+          }
+          __syncwarp();
         }
-        umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      if (elect_one()) umma_commit(&empty[s]);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
   } else if (warp >= 4 && my_items > 0) {
     const int ew = warp - 4;
     const int m = ew * 32 + lane;                               // accumulator row == TMEM lane

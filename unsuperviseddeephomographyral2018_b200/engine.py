@@ -60,6 +60,7 @@ class HomographyEngine(object):
         self.global_step = 0
         self.pg = process_group
         self.world_size = world_size
+        self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
         self.dropout_seed = 0x5EED0000 + (seed or 0)
         self.kernel_launches = 0   # kernels launched by the last forward/backward/update (counted, see _count)
 
@@ -138,14 +139,32 @@ class HomographyEngine(object):
         else:
             raise _lib.UdhError("loss_type %s has no CUDA backward yet (SURVEY §8f item 3)" % lt)
         out["_dh4p"] = dpred
-        check(lib.udh_cnn_bwd(self._p(self.params), self._p(batch["I1_aug"]), self._p(batch["I2_aug"]), self._p(dpred),
-                              self._p(self.grads), self._p(self.ws), self.ws_bytes, self.B, self.Pz, 1, self.numeric,
-                              ops._stream()), "udh_cnn_bwd")
+        args = (self._p(self.params), self._p(batch["I1_aug"]), self._p(batch["I2_aug"]), self._p(dpred), self._p(self.grads),
+                self._p(self.ws), self.ws_bytes, self.B, self.Pz, 1, self.numeric)
+        if self.world_size == 1:
+            check(lib.udh_cnn_bwd(*args, ops._stream()), "udh_cnn_bwd")
+            return
+        # Row G with overlap: the fully connected gradients (fc1 = 134 of the 137 MB) are complete after the head phase;
+        # their allreduce runs on the communication stream underneath the convolution backward.
+        cur = torch.cuda.current_stream()
+        check(lib.udh_cnn_bwd_phase(*args, _lib.BWD_HEAD, ops._stream()), "udh_cnn_bwd_phase(head)")
+        s16 = self.specs["model/fc1/fc1/weights"]
+        self._comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self._comm_stream):
+            torch.distributed.all_reduce(self.grads[s16.offset:], group=self.pg)          # fc1 w, fc1 b, fc2 w, fc2 b
+        check(lib.udh_cnn_bwd_phase(*args, _lib.BWD_CONVS, ops._stream()), "udh_cnn_bwd_phase(convs)")
+        self._head_reduced = True
 
     def allreduce_grads(self):
         """Row G: utils/utils.py:380-403 get_average_grads == allreduce(sum) here, 1/N folded into Adam."""
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+            if getattr(self, "_head_reduced", False):
+                s16 = self.specs["model/fc1/fc1/weights"]
+                torch.distributed.all_reduce(self.grads[:s16.offset], group=self.pg)      # the 8 conv layers (2.5 MB)
+                torch.cuda.current_stream().wait_stream(self._comm_stream)
+                self._head_reduced = False
+            else:
+                torch.distributed.all_reduce(self.grads, group=self.pg)
 
     def update(self):
         t = self.global_step + 1

@@ -53,4 +53,4 @@ def make_batch(B, seed=0, img_h=240, img_w=320, patch=128, rho=45, device="cuda"
     I1 = torch.gather(gray_I, 1, idx).reshape(B, patch, patch, 1).contiguous()
     I2 = torch.gather(gray_Ip, 1, idx).reshape(B, patch, patch, 1).contiguous()
     return dict(I1=I1, I2=I2, I1_aug=I1, I2_aug=I2, I_aug=I_n, I_prime_aug=Ip_n, pts1=pts1, gt=gt,
-                patch_indices=idx.to(torch.int32).contiguous())
+                patch_indices=idx.to(torch.int32).contiguous(), I_u8=I_u8, I_prime_u8=Ip_u8)

@@ -29,6 +29,12 @@ def pin_batch(batch):
     return out
 
 
+def pin_batch_u8(I_u8, I_prime_u8, pts1, gt):
+    """Host batch for HostStepper.step_u8: decoded uint8 images [B,Hh,W,3] + pts1/gt [B,8] in pinned memory."""
+    f = lambda t, dt: torch.as_tensor(t).detach().to("cpu").to(dt).contiguous().pin_memory()
+    return dict(I_u8=f(I_u8, torch.uint8), I_prime_u8=f(I_prime_u8, torch.uint8), pts1=f(pts1, torch.float32), gt=f(gt, torch.float32))
+
+
 class HostStepper(object):
     def __init__(self, engine: HomographyEngine, depth=2):
         self.eng = engine
@@ -46,6 +52,7 @@ class HostStepper(object):
         self.free = [torch.cuda.Event() for _ in range(depth)]
         self.done = [torch.cuda.Event() for _ in range(depth)]
         self.host_results = [torch.zeros(_lib.NMETRICS + _lib.NLOSSES, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.u8_slots = None
         self.i = 0
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -76,6 +83,44 @@ class HostStepper(object):
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ready[slot])
         out = self.eng.train_step(dst) if train else self.eng.forward(dst, train=False)
+        self.free[slot].record(cur)
+        res = torch.cat([out["h4p_metrics"], out["photo_losses"]])
+        self.host_results[slot].copy_(res, non_blocking=True)
+        self.d2h_bytes = res.numel() * 4
+        self.done[slot].record(cur)
+        prev = self._pending
+        self._pending = slot
+        self.i += 1
+        return self._results(prev) if prev is not None else None
+
+    def step_u8(self, host_batch, train=True):
+        """Same as step(), but the host hands over the DECODED uint8 images (what the reference dataloader holds before
+        normalising): normalisation, gray conversion and patch gather run on the device (udh_prep_inputs_u8)."""
+        import ctypes
+        from ._lib import check, lib
+        eng = self.eng
+        if self.u8_slots is None:
+            B, Hh, W = eng.B, eng.img_h, eng.img_w
+            self.u8_slots = [dict(I_u8=torch.empty(B, Hh, W, 3, device=eng.device, dtype=torch.uint8),
+                                  I_prime_u8=torch.empty(B, Hh, W, 3, device=eng.device, dtype=torch.uint8)) for _ in range(self.depth)]
+        slot = self.i % self.depth
+        dst, u8 = self.slots[slot], self.u8_slots[slot]
+        with torch.cuda.stream(self.copy_stream):
+            if self.i >= self.depth:
+                self.copy_stream.wait_event(self.free[slot])
+            u8["I_u8"].copy_(host_batch["I_u8"], non_blocking=True)
+            u8["I_prime_u8"].copy_(host_batch["I_prime_u8"], non_blocking=True)
+            dst["pts1"].copy_(host_batch["pts1"], non_blocking=True)
+            dst["gt"].copy_(host_batch["gt"], non_blocking=True)
+            self.ready[slot].record(self.copy_stream)
+        self.h2d_bytes = 2 * host_batch["I_u8"].numel() + 2 * host_batch["pts1"].numel() * 4
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ready[slot])
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        check(lib.udh_prep_inputs_u8(p(u8["I_u8"]), p(u8["I_prime_u8"]), p(dst["pts1"]), p(dst["I_aug"]), p(dst["I1_aug"]),
+                                     p(dst["I2_aug"]), p(dst["patch_indices"]), eng.B, eng.img_h, eng.img_w, eng.Pz,
+                                     ctypes.c_void_p(cur.cuda_stream)), "udh_prep_inputs_u8")
+        out = eng.train_step(dst) if train else eng.forward(dst, train=False)
         self.free[slot].record(cur)
         res = torch.cat([out["h4p_metrics"], out["photo_losses"]])
         self.host_results[slot].copy_(res, non_blocking=True)
