@@ -182,8 +182,9 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
   }
   TRY(bias_act_dropout(at<float>(ws, L.fc1_acc), params + PL.off[17], at<float>(ws, L.act[11]), at<float>(ws, L.fc1d),
                        train ? at<uint8_t>(ws, L.mask2) : nullptr, B, 1024, 1, 1, seed, 2, st));
-  // fc2, linear (:130-131)
-  TRY(sgemm_simt(at<float>(ws, L.fc1d), 1024, 1, params + PL.off[18], 8, 1, h4p, 8, B, 8, 1024, 1, 0, st));
+  // fc2, linear (:130-131): K = 1024 split 16 ways (2 CTAs walking K serially were latency bound), atomic accumulation
+  UDH_CUDA(cudaMemsetAsync(h4p, 0, (size_t)B * 8 * 4, st));
+  TRY(sgemm_simt(at<float>(ws, L.fc1d), 1024, 1, params + PL.off[18], 8, 1, h4p, 8, B, 8, 1024, 16, 0, st));
   TRY(bias_act_dropout(h4p, params + PL.off[19], h4p, nullptr, nullptr, B, 8, 0, 0, 0, 0, st));
   return UDH_OK;
 }

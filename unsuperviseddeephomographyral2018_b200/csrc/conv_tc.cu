@@ -75,6 +75,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   }
 }
 
+// all seven tensor-core layers in one launch (both directions): blockIdx.y = layer-1, blockIdx.z = direction
+struct PackTable { const float* w[7]; __nv_bfloat16* fwd[7]; __nv_bfloat16* dgr[7]; int cin[7], cout[7]; };
+__global__ void pack_all_weights_kernel(PackTable t, int do_fwd, int do_dgrad) {
+  const int L = blockIdx.y, dgrad = blockIdx.z;
+  if ((dgrad && !do_dgrad) || (!dgrad && !do_fwd)) return;
+  const int Cin = t.cin[L], Cout = t.cout[L];
+  const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout, CBk = K / 64, total = 9 * K * N;
+  const float* __restrict__ w = t.w[L];
+  __nv_bfloat16* __restrict__ dst = dgrad ? t.dgr[L] : t.fwd[L];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i & 63;
+    int r = i >> 6;
+    const int n = r % N; r /= N;
+    const int cb = r % CBk;
+    const int tap = r / CBk;
+    const int kc = cb * 64 + k;
+    dst[i] = __float2bfloat16_rn(dgrad ? w[((size_t)(8 - tap) * Cin + n) * Cout + kc] : w[((size_t)tap * Cin + kc) * Cout + n]);
+  }
+}
+
 // fp32 [B,H,W,C] -> bf16 padded [B,H+2,W+2,C] interior (borders untouched = zero)
 __global__ void pad_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C) {
   const int C4 = C >> 2;
@@ -396,9 +416,17 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
   char* tcw = at<char>(ws, tc_off);
   auto Pb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.P[i]); };
   {
+    // forward AND mirrored (dgrad) bf16 weight packs of the seven tensor-core layers, one launch per step
     ProfScope ps(PROF_TC_PREP, st);
-    for (int i = 1; i < 8; ++i)
-      TRY(pack_weights(params + poff[2 * i], reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), kConv[i].cin, kConv[i].cout, 0, st));
+    PackTable t;
+    for (int i = 1; i < 8; ++i) {
+      t.w[i - 1] = params + poff[2 * i];
+      t.fwd[i - 1] = reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]);
+      t.dgr[i - 1] = reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]);
+      t.cin[i - 1] = kConv[i].cin; t.cout[i - 1] = kConv[i].cout;
+    }
+    pack_all_weights_kernel<<<dim3(72, 7, 2), 256, 0, st>>>(t, 1, 1);
+    TRY(check_launch("pack_all_weights"));
   }
   {
     // conv1_1 (K = 18): fp32 CUDA-core kernel writing the padded bf16 stream directly
@@ -427,9 +455,7 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
   auto Pb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.P[i]); };
   auto Gb = [&](int i) { return reinterpret_cast<__nv_bfloat16*>(tcw + L.G[i]); };
   {
-    ProfScope ps(PROF_TC_PREP, st);
-    for (int i = 1; i < 8; ++i)
-      TRY(pack_weights(params + poff[2 * i], reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]), kConv[i].cin, kConv[i].cout, 1, st));
+    ProfScope ps(PROF_TC_PREP, st);        // (the mirrored weight packs were made by the forward of this step)
     TRY(pad_cast(gA, Gb(7), B, P / 8, P / 8, 128, st));
   }
   for (int i = 7; i >= 0; --i) {

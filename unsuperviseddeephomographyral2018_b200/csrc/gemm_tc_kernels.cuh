@@ -124,7 +124,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * 256 + c * 32), v);
         if (m < g.M) {
           const int n0 = nt * 256 + c * 32;
-          if (ATOMIC) {
+          if (ATOMIC && n0 + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red_add_v4(crow + c * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else if (ATOMIC) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + j < g.N) atomicAdd(crow + c * 32 + j, v[j]);

@@ -131,6 +131,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-byte vector reduction into global memory (REDG.E.ADD.F32x4): one L2 atomic transaction for four floats.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle.  start: smem byte address; lbo/sbo in bytes;
 // base_offset = (start >> 7) & 7 when the start is not on a 1024-byte swizzle-pattern boundary.
