@@ -27,9 +27,20 @@ __device__ __forceinline__ void load_planes(float* tile, const float* __restrict
   }
 }
 
+// spread the low 16 bits of x to the even bit positions
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
 __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict__ I1, const float* __restrict__ I2,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        __nv_bfloat16* __restrict__ out, int B, int H, int W) {
+                                                        __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ mask_out, int B, int H,
+                                                        int W) {
   extern __shared__ float tile[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = W + 2, plane = (ROWS + 2) * pitch;
@@ -58,6 +69,7 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
         xw[ci][ky][2] = tile[ci * plane + (warp + ky) * pitch + 1];
       }
     __nv_bfloat16* orow = out + (((size_t)n * (H + 2) + y + 1) * (W + 2) + 1) * 64 + 2 * lane;
+    uint32_t keep_e = 0, keep_o = 0;
 #pragma unroll 4
     for (int x = 0; x < W; ++x) {
 #pragma unroll
@@ -79,6 +91,19 @@ __global__ void __launch_bounds__(256) conv1_fwd_kernel(const float* __restrict_
           }
       const __nv_bfloat162 p = __floats2bfloat162_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
       *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)x * 64) = p;
+      if (mask_out) {
+        // 1-bit ReLU mask, channel c -> bit c%32 of word c/32 (lane l owns channels 2l, 2l+1).  Lane x%32 keeps the two
+        // ballots of position x; every 32 positions each lane packs and stores one position: a coalesced 256-byte store.
+        const uint32_t e = __ballot_sync(0xffffffffu, __low2float(p) > 0.f), o = __ballot_sync(0xffffffffu, __high2float(p) > 0.f);
+        if ((x & 31) == lane) { keep_e = e; keep_o = o; }
+        if ((x & 31) == 31) {
+          const size_t q = ((size_t)n * (H + 2) + y + 1) * (W + 2) + (x - 31 + lane) + 1;
+          uint2 mw;
+          mw.x = spread16(keep_e) | (spread16(keep_o) << 1);
+          mw.y = spread16(keep_e >> 16) | (spread16(keep_o >> 16) << 1);
+          *reinterpret_cast<uint2*>(mask_out + q * 2) = mw;
+        }
+      }
     }
   }
 }
@@ -156,12 +181,12 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
 
 }  // namespace
 
-int conv1_fwd_bf16(const float* I1, const float* I2, const float* w, const float* bias, __nv_bfloat16* out_pad, int B, int H, int W,
-                   cudaStream_t st) {
-  UDH_REQUIRE(H % ROWS == 0 && W >= 8, "conv1_fwd_bf16: unsupported shape");
+int conv1_fwd_bf16(const float* I1, const float* I2, const float* w, const float* bias, __nv_bfloat16* out_pad, uint32_t* mask_out,
+                   int B, int H, int W, cudaStream_t st) {
+  UDH_REQUIRE(H % ROWS == 0 && W % 32 == 0, "conv1_fwd_bf16: unsupported shape");
   const size_t smem = (size_t)2 * (ROWS + 2) * (W + 2) * sizeof(float);
   const int tiles = B * (H / ROWS);
-  conv1_fwd_kernel<<<tiles < 148 * 8 ? tiles : 148 * 8, 256, smem, st>>>(I1, I2, w, bias, out_pad, B, H, W);
+  conv1_fwd_kernel<<<tiles < 148 * 8 ? tiles : 148 * 8, 256, smem, st>>>(I1, I2, w, bias, out_pad, mask_out, B, H, W);
   return check_launch("conv1_fwd_bf16");
 }
 

@@ -7,6 +7,7 @@
 #include "conv_tc_kernels.cuh"
 #include "wgrad_tc_kernels.cuh"
 #include "gemm_tc_kernels.cuh"
+#include "conv1_tc_kernels.cuh"
 
 namespace udh {
 
@@ -24,6 +25,7 @@ struct TcLayout {
   size_t G[11];      // padded bf16 gradients w.r.t. the same tensors (pre-activation for convs)
   size_t numel[11];  // padded element counts
   size_t wf[8], wd[8];   // packed bf16 weights, forward / dgrad (rotated)
+  size_t Mb[8];      // 1-bit ReLU masks [Q][C/32] uint32 of the conv outputs a dgrad needs (layers 0, 2, 4, 6)
   size_t fc_x, fc_w, fc_dy;   // bf16 copies for the fc1 GEMMs: x [B,F], W [F,1024], dy [B,1024]
   size_t total;
   TcLayout(int B, int P_) {
@@ -39,6 +41,7 @@ struct TcLayout {
     for (int i = 0; i < 11; ++i) P[i] = take(numel[i] * 2);
     for (int i = 0; i < 11; ++i) G[i] = take(numel[i] * 2);
     for (int i = 0; i < 8; ++i) { wf[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); wd[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); }
+    for (int i = 0; i < 8; ++i) Mb[i] = (i % 2 == 0) ? take(numel[i] / 8) : 0;
     const size_t feat = (size_t)(P_ / 8) * (P_ / 8) * 128;
     fc_x = take((size_t)B * feat * 2);
     fc_w = take(feat * 1024 * 2);
@@ -204,9 +207,24 @@ __global__ void pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, const
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI>
+int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const CUtensorMap& tmW, const CUtensorMap& tmOut,
+                     const tc::ConvGeom& g, const float* bias, const __nv_bfloat16* mask_src, const uint32_t* mask_bits,
+                     uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, size_t smem, cudaStream_t st) {
+  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = g.num_items < sms ? g.num_items : sms;
+  kern<<<grid, 256, smem, st>>>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
+  return check_launch("tc_conv_kernel");
+}
+
 template <int N_OUT, int CB, int T, bool WRES>
 int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const __nv_bfloat16* mask_src,
-                __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, cudaStream_t st) {
+                const uint32_t* mask_bits, uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W,
+                cudaStream_t st) {
   tc::ConvGeom g;
   g.B = B; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
   g.Q = B * g.Hp * g.Wp;
@@ -215,7 +233,7 @@ int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* b
   g.num_items = (tiles + T - 1) / T;
   g.abuf_rows = T * 128 + 2 * g.hh;
   const int Cin = CB * 64;
-  CUtensorMap tmA128, tmAhh, tmW;
+  CUtensorMap tmA128, tmAhh, tmW, tmOut;
   uint64_t dimsA[2] = {(uint64_t)Cin, (uint64_t)g.Q}, strA[2] = {2, (uint64_t)Cin * 2};
   uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh};
   TRY(tc::make_tmap_bf16(&tmA128, x, 2, dimsA, strA, box128));
@@ -223,25 +241,28 @@ int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* b
   uint64_t dimsW[2] = {64, (uint64_t)9 * CB * N_OUT}, strW[2] = {2, 128};
   uint32_t boxW[2] = {64, (uint32_t)N_OUT};
   TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
-  const size_t smem = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows);
+  uint64_t dimsO[2] = {(uint64_t)N_OUT, (uint64_t)g.Q}, strO[2] = {2, (uint64_t)N_OUT * 2};
+  uint32_t boxO[2] = {64, 32};
+  TRY(tc::make_tmap_bf16(&tmOut, out_bf, 2, dimsO, strO, boxO));
+  // TMA-store epilogue when its 16 KiB staging block still fits next to the operand buffers
+  const size_t smem_tma = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows, true);
+  if (out_bf && smem_tma <= 232448)
+    return launch_conv_impl<N_OUT, CB, T, WRES, true>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu,
+                                                      smem_tma, st);
+  const size_t smem = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows, false);
   UDH_REQUIRE(smem <= 232448, "tc conv: %zu bytes of shared memory exceed the 227 KiB limit", smem);
-  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES>;
-  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = g.num_items < sms ? g.num_items : sms;
-  kern<<<grid, 256, smem, st>>>(tmA128, tmAhh, tmW, g, bias, mask_src, out_bf, out_f32, relu);
-  return check_launch("tc_conv_kernel");
+  return launch_conv_impl<N_OUT, CB, T, WRES, false>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu,
+                                                     smem, st);
 }
 
 // one 3x3 conv on padded bf16 streams; (cin -> cout) selects the kernel instance
 int tc_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const __nv_bfloat16* mask_src,
-            __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, int cin, int cout, cudaStream_t st) {
-  if (cin == 64 && cout == 64) return launch_conv<64, 1, 2, true>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
-  if (cin == 64 && cout == 128) return launch_conv<128, 1, 1, true>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
-  if (cin == 128 && cout == 64) return launch_conv<64, 2, 2, false>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
-  if (cin == 128 && cout == 128) return launch_conv<128, 2, 2, false>(x, wpk, bias, mask_src, out_bf, out_f32, relu, B, H, W, st);
+            const uint32_t* mask_bits, uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, int cin,
+            int cout, cudaStream_t st) {
+  if (cin == 64 && cout == 64) return launch_conv<64, 1, 2, true>(x, wpk, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 64 && cout == 128) return launch_conv<128, 1, 1, true>(x, wpk, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 128 && cout == 64) return launch_conv<64, 2, 2, false>(x, wpk, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu, B, H, W, st);
+  if (cin == 128 && cout == 128) return launch_conv<128, 2, 2, false>(x, wpk, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu, B, H, W, st);
   set_error("tc_conv: unsupported channel combination %d -> %d", cin, cout);
   return UDH_ENOSUP;
 }
@@ -393,6 +414,39 @@ int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, cons
   return check_launch("tc_gemm_kernel");
 }
 
+// conv1_1 on the tensor pipe (im2col tile built in shared memory), see conv1_tc_kernels.cuh
+int conv1_tc_fwd(const float* I1, const float* I2, const float* w, const float* bias, __nv_bfloat16* out_pad, uint32_t* mask_out, int B,
+                 int H, int W, cudaStream_t st) {
+  UDH_REQUIRE(W % 128 == 0, "conv1_tc_fwd: image width must be a multiple of 128");
+  tc::Conv1Geom g{B, H, W, B * H * (W / 128)};
+  CUtensorMap tmOut;
+  const uint64_t Q = (uint64_t)B * (H + 2) * (W + 2);
+  uint64_t dims[2] = {64, Q}, str[2] = {2, 128};
+  uint32_t box[2] = {64, 32};
+  TRY(tc::make_tmap_bf16(&tmOut, out_pad, 2, dims, str, box));
+  const size_t smem = 1024 + 2 * 16384 + 8192 + 16384 + 256;
+  UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = g.tiles < 296 ? g.tiles : 296;
+  tc::conv1_tc_fwd_kernel<<<grid, 160, smem, st>>>(tmOut, g, I1, I2, w, bias, mask_out);
+  return check_launch("conv1_tc_fwd_kernel");
+}
+
+int conv1_tc_wgrad(const float* I1, const float* I2, const __nv_bfloat16* G_pad, float* dW, float* db, int B, int H, int W,
+                   cudaStream_t st) {
+  UDH_REQUIRE(W % 128 == 0, "conv1_tc_wgrad: image width must be a multiple of 128");
+  tc::Conv1Geom g{B, H, W, B * H * (W / 128)};
+  CUtensorMap tmG;
+  const uint64_t Q = (uint64_t)B * (H + 2) * (W + 2);
+  uint64_t dims[2] = {64, Q}, str[2] = {2, 128};
+  uint32_t box[2] = {64, 128};
+  TRY(tc::make_tmap_bf16(&tmG, G_pad, 2, dims, str, box));
+  const size_t smem = 1024 + 4 * 16384 + 256;
+  UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = g.tiles < 296 ? g.tiles : 296;
+  tc::conv1_tc_wgrad_kernel<<<grid, 160, smem, st>>>(tmG, g, I1, I2, dW, db);
+  return check_launch("conv1_tc_wgrad_kernel");
+}
+
 // input tensor index (into P / G) of conv layer i (i >= 1)
 inline int input_of(int i) { return (i == 2 || i == 4 || i == 6) ? 8 + (i - 2) / 2 : i - 1; }
 
@@ -429,15 +483,16 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
     TRY(check_launch("pack_all_weights"));
   }
   {
-    // conv1_1 (K = 18): fp32 CUDA-core kernel writing the padded bf16 stream directly
+    // conv1_1 (K = 18): im2col tile in shared memory + tcgen05, writing the padded bf16 stream and its 1-bit ReLU mask
     ProfScope ps(PROF_CONV_FWD0, st);
-    TRY(conv1_fwd_bf16(I1, I2, params + poff[0], params + poff[1], Pb(0), B, P, P, st));
+    TRY(conv1_tc_fwd(I1, I2, params + poff[0], params + poff[1], Pb(0), reinterpret_cast<uint32_t*>(tcw + L.Mb[0]), B, P, P, st));
   }
   for (int i = 1; i < 8; ++i) {
     const int s = P / kConv[i].div;
     {
       ProfScope ps(PROF_CONV_FWD0 + i, st);
-      TRY(tc_conv(Pb(input_of(i)), reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), params + poff[2 * i + 1], nullptr, Pb(i),
+      TRY(tc_conv(Pb(input_of(i)), reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), params + poff[2 * i + 1], nullptr, nullptr,
+                  (i % 2 == 0) ? reinterpret_cast<uint32_t*>(tcw + L.Mb[i]) : nullptr, Pb(i),
                   i == 7 ? at<float>(ws, act_off[7]) : nullptr, 1, B, s, s, kConv[i].cin, kConv[i].cout, st));
     }
     if (i == 1 || i == 3 || i == 5) {
@@ -464,8 +519,8 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     {
       ProfScope ps(PROF_CONV_WGRAD0 + i, st);
       if (i == 0) {
-        // conv1_1 (Cin = 2): fp32 CUDA-core wgrad reading the bf16 gradient stream directly
-        TRY(conv1_wgrad_bf16(I1, I2, Gb(0), grads + poff[0], grads + poff[1], B, s, s, st));
+        // conv1_1 (Cin = 2): im2col tile (MN-major A, M = 64) x gradient rows by TMA, bias gradient from the ones column
+        TRY(conv1_tc_wgrad(I1, I2, Gb(0), grads + poff[0], grads + poff[1], B, s, s, st));
       } else {
         TRY(tc_wgrad(Pb(input_of(i)), Gb(i), grads + poff[2 * i], grads + poff[2 * i + 1], B, s, s, cin, cout, st));
       }
@@ -476,8 +531,9 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     {
       ProfScope ps(PROF_CONV_DGRAD0 + i, st);
       // dgrad = conv of G[i] with the mirrored kernel; ReLU mask of the layer below fused unless a pool sits between
-      TRY(tc_conv(Gb(i), reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]), nullptr, below_is_pool ? nullptr : Pb(below), Gb(below),
-                  nullptr, 0, B, s, s, cout, cin, st));
+      TRY(tc_conv(Gb(i), reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]), nullptr, nullptr,
+                  below_is_pool ? nullptr : reinterpret_cast<const uint32_t*>(tcw + L.Mb[below]), nullptr, Gb(below), nullptr, 0, B, s, s,
+                  cout, cin, st));
     }
     if (below_is_pool) {
       ProfScope ps(PROF_POOL_BWD, st);
@@ -533,7 +589,7 @@ int tc_debug_conv(const float* x, const float* w, const float* bias, float* out,
   UDH_CUDA(cudaMemsetAsync(scratch, 0, tc_debug_scratch_bytes(B, H, W, cin, cout), st));
   TRY(pad_cast(x, xp, B, H, W, kin, st));
   TRY(pack_weights(w, wp, cin, cout, dgrad, st));
-  TRY(tc_conv(xp, wp, bias, nullptr, op, out, relu, B, H, W, kin, kout, st));
+  TRY(tc_conv(xp, wp, bias, nullptr, nullptr, nullptr, op, out, relu, B, H, W, kin, kout, st));
   return UDH_OK;
 }
 

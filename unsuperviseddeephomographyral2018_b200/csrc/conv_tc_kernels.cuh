@@ -31,25 +31,33 @@ struct ConvGeom {
 
 constexpr int kNumWStages = 3;
 
+constexpr int kEpiStageBytes = 4 * 32 * 128;   // TMA-store staging: 32 rows x 128 B per epilogue warp
+
 template <int N_OUT, int CB, int T, bool WRES>
 struct ConvSmem {
   static constexpr int kWBytesPerKb = N_OUT * 128;
   static constexpr int kWBytes = WRES ? 9 * CB * kWBytesPerKb : kNumWStages * kWBytesPerKb;
-  static size_t bytes(int abuf_rows) { return 1024 + (size_t)2 * CB * abuf_rows * 128 + kWBytes + 256; }
+  static size_t bytes(int abuf_rows, bool tma_epi) {
+    return 1024 + (size_t)2 * CB * abuf_rows * 128 + kWBytes + (tma_epi ? kEpiStageBytes : 0) + 256;
+  }
 };
 
-template <int N_OUT, int CB, int T, bool WRES>
+// TMA_EPI: the epilogue stages each warp's 32 x 64-channel bf16 block in (swizzled) shared memory and writes it with one
+// TMA store (full 128-byte lines, asynchronous); the ReLU-mask block of a dgrad is fetched the same way round (coalesced
+// 512-byte warp loads into the staging block).  Without it each lane stores its own 64 bytes at a 128-byte stride.
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI>
 __global__ void __launch_bounds__(256, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
-               const __grid_constant__ CUtensorMap tmW, const ConvGeom g, const float* __restrict__ bias,
-               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ out_bf, float* __restrict__ out_f32,
-               int relu) {
+               const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
+               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask_src, const uint32_t* __restrict__ mask_bits,
+               uint32_t* __restrict__ mask_out, __nv_bfloat16* __restrict__ out_bf, float* __restrict__ out_f32, int relu) {
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   const int abuf_bytes = g.abuf_rows * 128;                       // one 64-channel block of one buffer
   uint8_t* sA = base;                                             // [2][CB][abuf_rows][128]
   uint8_t* sW = base + (size_t)2 * CB * abuf_bytes;               // resident: [9*CB][N_OUT][128]; streamed: [stages][N_OUT][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + ConvSmem<N_OUT, CB, T, WRES>::kWBytes);
+  uint8_t* sEpi = sW + ConvSmem<N_OUT, CB, T, WRES>::kWBytes;      // [4 warps][32 rows][128 B] (TMA_EPI only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + (TMA_EPI ? kEpiStageBytes : 0));
   uint64_t* a_full = bars;            // [2]
   uint64_t* a_empty = bars + 2;       // [2]
   uint64_t* t_full = bars + 4;        // [2]
@@ -71,7 +79,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     for (int i = 0; i < kNumWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA128); prefetch_tmap(&tmAhh); prefetch_tmap(&tmW); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmA128); prefetch_tmap(&tmAhh); prefetch_tmap(&tmW); if (TMA_EPI) prefetch_tmap(&tmOut); }
   if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -166,6 +174,120 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
+    if (TMA_EPI) {
+      const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
+      const int HpWp = g.Hp * g.Wp;
+      uint8_t* stg = sEpi + ew * 4096;              // this warp's 32 x 128 B staging block (1024-byte aligned)
+      const uint32_t my_row = smem_u32(stg) + lane * 128;
+      const int sw = lane & 7;                      // 128-byte swizzle phase of this lane's row
+      bool store_pending = false;
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        mbar_wait(&t_full[b], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+          const int q0w = (item * T + t) * 128 + ew * 32;       // first position of this warp's block
+          const int q = q0w + lane;
+          const int n = q / HpWp, rem = q - n * HpWp;
+          const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
+          const bool valid = q < g.Q && xp >= 1 && xp <= g.W && yp >= 1 && yp <= g.H;
+          const size_t o_f32 = (((size_t)n * g.H + (yp - 1)) * g.W + (xp - 1)) * N_OUT;
+          // ReLU-backward mask of a dgrad as 1 bit / element (written by the forward of the layer below): one 8/16-byte
+          // load per position instead of a 128/256-byte bf16 row
+          uint32_t mb[N_OUT / 32];
+#pragma unroll
+          for (int i = 0; i < N_OUT / 32; ++i) mb[i] = (mask_bits && q < g.Q) ? __ldg(mask_bits + (size_t)q * (N_OUT / 32) + i) : 0u;
+          uint32_t mo[N_OUT / 32];
+#pragma unroll
+          for (int hf = 0; hf < N_OUT / 64; ++hf) {
+            if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
+            if (mask_src) {
+              // 32 rows x 128 B of the mask stream, 4 rows (512 contiguous bytes) per warp instruction
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = i * 4 + (lane >> 3), ch = lane & 7;
+                uint4 m = make_uint4(0, 0, 0, 0);
+                if (q0w + row < g.Q) m = __ldg(reinterpret_cast<const uint4*>(mask_src + (size_t)(q0w + row) * N_OUT + hf * 64) + ch);
+                *reinterpret_cast<uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = m;
+              }
+              __syncwarp();
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int c = hf * 2 + c2;
+              float v[32];
+              tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
+              if (bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
+                  v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                }
+              }
+              if (relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              if (mask_bits) {
+                const uint32_t w = mb[c];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+              }
+              if (mask_out) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+                mo[c] = w;
+              }
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const uint32_t addr = my_row + (uint32_t)(((c2 * 4 + j4) ^ sw) << 4);
+                if (mask_src) {
+                  uint4 m;
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(addr));
+                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                  for (int h = 0; h < 4; ++h) {
+                    const uint32_t lo = mw[h] & 0xFFFFu, hi = mw[h] >> 16;     // bf16 > 0 <=> non-zero magnitude, sign clear
+                    if (!(lo != 0 && !(lo & 0x8000u))) v[j4 * 8 + h * 2] = 0.f;
+                    if (!(hi != 0 && !(hi & 0x8000u))) v[j4 * 8 + h * 2 + 1] = 0.f;
+                  }
+                }
+                uint4 pk = make_uint4(0, 0, 0, 0);                             // border / out-of-range positions store zeros
+                if (valid) {
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+                  __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+                  __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                }
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+              }
+              if (out_f32 && valid) {
+                float4* fp = reinterpret_cast<float4*>(out_f32 + o_f32 + c * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) fp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              }
+            }
+            fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0 && q0w < g.Q) { tma_store_2d(&tmOut, stg, hf * 64, q0w); bulk_commit(); }
+            store_pending = true;
+          }
+          if (mask_out && q < g.Q) {
+#pragma unroll
+            for (int i = 0; i < N_OUT / 32; ++i) mask_out[(size_t)q * (N_OUT / 32) + i] = valid ? mo[i] : 0u;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[b]);
+      }
+      if (lane == 0) bulk_wait0();
+      __syncwarp();
+    } else {
     const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
     const int HpWp = g.Hp * g.Wp;
     for (int it = 0; it < my_items; ++it) {
@@ -196,6 +318,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
             if (relu) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (mask_bits) {
+              const uint32_t w = __ldg(mask_bits + (size_t)q * (N_OUT / 32) + c);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+            }
+            if (mask_out) {
+              uint32_t w = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+              mask_out[(size_t)q * (N_OUT / 32) + c] = w;
             }
             if (mask_src) {
               const uint4* mp = reinterpret_cast<const uint4*>(mask_src + o_pad + c * 32);
@@ -238,6 +371,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       mbar_arrive(&t_empty[b]);
     }
   }
+    }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
