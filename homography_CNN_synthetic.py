@@ -225,7 +225,7 @@ def test_homography(args):
     h_losses_array = []
     step = 0
     for step in range(steps):
-        out = eng.forward(loader.next_batch(), train=False)
+        out = eng.eval_step(loader.next_batch())
         d = eng.losses_dict(out)
         vals = torch.tensor([d["bounded_h_loss"], d["rec_loss"], d["ssim_loss"], d["l1_loss"], d["num_fail"]], device="cuda", dtype=torch.float64)
         if world > 1:

@@ -151,6 +151,33 @@ size_t udh_param_total_floats(int P);
 int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                   float eps, float grad_scale, int zero_grad, void* stream);
 
+/* ---- one call per step -------------------------------------------------------------------------------------------
+ * The reference runs a step as ONE sess.run([apply_grad_opt, losses...]) (homography_CNN_synthetic.py:335-345).
+ * udh_step_forward_backward enqueues regressor forward, h4p losses (:274-288), DLT (:169-250), fused warp + all
+ * photometric diagnostics (:252-269,291-296) and the backward of the selected loss on `stream`; the caller then runs the
+ * gradient allreduce (N > 1) and udh_adam_step.  Every output buffer is caller-owned and reused step after step. */
+#define UDH_STEP_ALL 0      /* forward + full backward                                                         */
+#define UDH_STEP_FWD_HEAD 1 /* forward + backward of the fully connected head (then allreduce fc grads ...)    */
+#define UDH_STEP_CONVS 2    /* ... while this runs: backward of the conv stack                                 */
+#define UDH_STEP_FWD_ONLY 3 /* evaluation: forward, losses, metrics                                            */
+#define UDH_STEP_LOSS_H 0
+#define UDH_STEP_LOSS_L1 1
+#define UDH_STEP_LOSS_REC 2
+#define UDH_STEP_LOSS_L1_SMOOTH 3
+typedef struct {
+  int B, P, img_h, img_w, C;      /* batch, patch size, image size, channels of I_aug (1 or 3) */
+  int numeric_mode, loss_type, train;
+  uint64_t seed;                  /* dropout seed of this step */
+  const float* params; float* grads; void* ws; size_t ws_bytes;
+  const float *I1, *I2, *I_aug, *pts1, *gt;   /* gt may be NULL (no h_loss / metrics) */
+  const int32_t* patch_indices; int64_t idx_stride;
+  float *h4p, *H, *pred_I2;       /* [B,8], [B,9], [B,P,P] (pred_I2 may be NULL: then no SSIM) */
+  float *dh4p, *dH, *scratch;     /* [B,8], [B,9], [B,9] */
+  double* sums;                   /* [UDH_NSUMS] */
+  float *photo_losses, *h4p_metrics, *per_sample;   /* [UDH_NLOSSES], [UDH_NMETRICS], [B] or NULL */
+} udh_step_args;
+int udh_step_forward_backward(const udh_step_args* args, int phase, void* stream);
+
 /* ---- device-side input pipeline (dataloader.py:99-100,172-177,203-227) ------------------------
  * I, I_prime: uint8 [B,img_h,img_w,3] decoded images; pts1 [B,8].  Writes the post-dataloader tensors the step
  * consumes: I_aug fp32 [B,img_h,img_w,3] (normalised with I's statistics), gray patches I1, I2 fp32 [B,P,P] at

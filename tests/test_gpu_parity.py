@@ -365,3 +365,19 @@ def test_device_input_pipeline_and_synthetic_generator(udh):
     for k in ("h_loss", "l1_loss", "rec_loss"):
         assert abs(r_f32[k] - d[k]) <= 1e-5 * max(1, abs(d[k])) and abs(r_u8[k] - d[k]) <= 1e-4 * max(1, abs(d[k])), k
     assert st2.h2d_bytes < st.h2d_bytes / 2
+
+
+def test_one_call_step_equals_separate_calls(udh):
+    """udh_step_forward_backward (one C call per step) == forward() + backward() through the individual entry points."""
+    for loss_type in ("h_loss", "l1_loss"):
+        batch = dev(O.make_batch(2, 3))
+        e1 = udh.engine.HomographyEngine(3, seed=1, loss_type=loss_type, lr=5e-4)
+        e2 = udh.engine.HomographyEngine(3, seed=1, loss_type=loss_type, lr=5e-4)
+        o1 = e1.forward(batch, train=True); e1.backward(batch, o1); g1 = e1.grads.clone(); d1 = e1.losses_dict(o1); e1.update()
+        o2 = e2.train_step(batch); d2 = e2.losses_dict(o2)
+        assert (o1["pred_h4p"] - o2["pred_h4p"]).abs().max().item() < 1e-6
+        for k in d1:
+            assert abs(d1[k] - d2[k]) <= 1e-5 * max(1.0, abs(d1[k])), k
+        assert (e1.params - e2.params).abs().max().item() <= 1e-6 and e2.global_step == 1
+        ev = e2.losses_dict(e2.eval_step(batch))
+        assert abs(ev["l1_loss"] - e2.losses_dict(e2.forward(batch, train=False))["l1_loss"]) < 1e-6

@@ -17,6 +17,22 @@ NSUMS, NLOSSES, NMETRICS = 8, 8, 4
 L_REC, L_SSIM, L_L1, L_L1_SMOOTH, L_NCC = 0, 1, 2, 3, 4
 M_H_LOSS, M_BOUNDED_H_LOSS, M_NUM_FAIL, M_ACE = 0, 1, 2, 3
 
+class StepArgs(ctypes.Structure):
+    """udh_step_args (include/udh.h)."""
+    _fields_ = [("B", c_int), ("P", c_int), ("img_h", c_int), ("img_w", c_int), ("C", c_int),
+                ("numeric_mode", c_int), ("loss_type", c_int), ("train", c_int), ("seed", c_uint64),
+                ("params", c_void_p), ("grads", c_void_p), ("ws", c_void_p), ("ws_bytes", c_size_t),
+                ("I1", c_void_p), ("I2", c_void_p), ("I_aug", c_void_p), ("pts1", c_void_p), ("gt", c_void_p),
+                ("patch_indices", c_void_p), ("idx_stride", c_int64),
+                ("h4p", c_void_p), ("H", c_void_p), ("pred_I2", c_void_p),
+                ("dh4p", c_void_p), ("dH", c_void_p), ("scratch", c_void_p), ("sums", c_void_p),
+                ("photo_losses", c_void_p), ("h4p_metrics", c_void_p), ("per_sample", c_void_p)]
+
+
+STEP_ALL, STEP_FWD_HEAD, STEP_CONVS, STEP_FWD_ONLY = 0, 1, 2, 3
+STEP_LOSS = {"h_loss": 0, "l1_loss": 1, "rec_loss": 2, "l1_smooth_loss": 3}
+
+
 # name -> (restype, argtypes); every symbol include/udh.h declares
 SIGNATURES = {
     "udh_version": (c_int, []),
@@ -51,6 +67,7 @@ SIGNATURES = {
     "udh_debug_tc_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p]),
     "udh_debug_tc_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "udh_step_forward_backward": (c_int, [POINTER(StepArgs), c_int, c_void_p]),
     "udh_prep_inputs_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                    c_void_p]),
     "udh_launch_count": (c_ulonglong, []),

@@ -61,6 +61,13 @@ class HomographyEngine(object):
         self.pg = process_group
         self.world_size = world_size
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
+        # static per-step outputs of the one-call step (udh_step_forward_backward): reused every step
+        B, Pz, dev = self.B, self.Pz, self.device
+        self._sb = dict(h4p=torch.zeros(B, 8, device=dev), H=torch.zeros(B, 3, 3, device=dev), pred=torch.zeros(B, Pz, Pz, 1, device=dev),
+                        dh4p=torch.zeros(B, 8, device=dev), dH=torch.zeros(B, 3, 3, device=dev), scratch=torch.zeros(B * 9, device=dev),
+                        sums=torch.zeros(_lib.NSUMS, device=dev, dtype=torch.float64), photo=torch.zeros(_lib.NLOSSES, device=dev),
+                        metrics=torch.zeros(_lib.NMETRICS, device=dev), per=torch.zeros(B, device=dev))
+        self._args = _lib.StepArgs()
         self.dropout_seed = 0x5EED0000 + (seed or 0)
         self.kernel_launches = 0   # kernels launched by the last forward/backward/update (counted, see _count)
 
@@ -175,12 +182,60 @@ class HomographyEngine(object):
         self.global_step += 1
         return lr_t
 
+    def _fill_args(self, batch, train):
+        a, sb = self._args, self._sb
+        I_aug = batch["I_aug"]
+        a.B, a.P, a.img_h, a.img_w, a.C = self.B, self.Pz, I_aug.shape[1], I_aug.shape[2], I_aug.shape[3]
+        a.numeric_mode, a.train = self.numeric, int(train)
+        a.loss_type = _lib.STEP_LOSS.get(self.loss_type, -1)
+        a.seed = self.dropout_seed + self.global_step
+        dp = lambda t: t.data_ptr() if t is not None else None
+        a.params, a.grads, a.ws, a.ws_bytes = dp(self.params), dp(self.grads), dp(self.ws), self.ws_bytes
+        a.I1, a.I2, a.I_aug, a.pts1, a.gt = dp(batch["I1_aug"]), dp(batch["I2_aug"]), dp(I_aug), dp(batch["pts1"]), dp(batch.get("gt"))
+        pi = batch.get("patch_indices")
+        a.patch_indices = dp(pi)
+        a.idx_stride = 0 if pi is None else (pi.stride(0) if pi.dim() > 1 else 1)
+        a.h4p, a.H, a.pred_I2 = dp(sb["h4p"]), dp(sb["H"]), dp(sb["pred"])
+        a.dh4p, a.dH, a.scratch, a.sums = dp(sb["dh4p"]), dp(sb["dH"]), dp(sb["scratch"]), dp(sb["sums"])
+        a.photo_losses, a.h4p_metrics, a.per_sample = dp(sb["photo"]), dp(sb["metrics"]), dp(sb["per"])
+        return a
+
+    def _step_out(self, batch):
+        sb = self._sb
+        out = OrderedDict(pred_h4p=sb["h4p"], H_mat=sb["H"], pred_I2=sb["pred"], photo_losses=sb["photo"], _sums=sb["sums"])
+        if batch.get("gt") is not None:
+            out["h4p_metrics"], out["batch_h_loss"] = sb["metrics"], sb["per"]
+        return out
+
     def train_step(self, batch):
-        out = self.forward(batch, train=True)
-        self.backward(batch, out)
-        self.allreduce_grads()
+        """One optimiser step.  The whole forward/backward is ONE C call (udh_step_forward_backward); result tensors are
+        the engine's static buffers (valid until the next step)."""
+        if self.loss_type not in _lib.STEP_LOSS:
+            raise _lib.UdhError("loss_type %s has no CUDA backward yet (SURVEY §8f item 3)" % self.loss_type)
+        a = self._fill_args(batch, True)
+        st = ops._stream()
+        if self.world_size == 1:
+            check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_ALL, st), "udh_step_forward_backward")
+        else:
+            # Row G with overlap: allreduce the fully connected gradients (134 of 137 MB) under the conv backward
+            cur = torch.cuda.current_stream()
+            check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_FWD_HEAD, st), "udh_step_forward_backward(head)")
+            s16 = self.specs["model/fc1/fc1/weights"]
+            self._comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._comm_stream):
+                torch.distributed.all_reduce(self.grads[s16.offset:], group=self.pg)
+            check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_CONVS, st), "udh_step_forward_backward(convs)")
+            torch.distributed.all_reduce(self.grads[:s16.offset], group=self.pg)
+            cur.wait_stream(self._comm_stream)
+        out = self._step_out(batch)
         out["lr"] = self.update()
         return out
+
+    def eval_step(self, batch):
+        """Forward + all losses / test metrics in one C call (static result buffers)."""
+        a = self._fill_args(batch, False)
+        check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_FWD_ONLY, ops._stream()), "udh_step_forward_backward(eval)")
+        return self._step_out(batch)
 
     # ------------------------------------------------------------------ test helpers
     def dropout_masks(self):

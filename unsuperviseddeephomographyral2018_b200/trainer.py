@@ -82,7 +82,7 @@ class HostStepper(object):
         self.h2d_bytes = nbytes
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ready[slot])
-        out = self.eng.train_step(dst) if train else self.eng.forward(dst, train=False)
+        out = self.eng.train_step(dst) if train else self.eng.eval_step(dst)
         self.free[slot].record(cur)
         res = torch.cat([out["h4p_metrics"], out["photo_losses"]])
         self.host_results[slot].copy_(res, non_blocking=True)
@@ -120,7 +120,7 @@ class HostStepper(object):
         check(lib.udh_prep_inputs_u8(p(u8["I_u8"]), p(u8["I_prime_u8"]), p(dst["pts1"]), p(dst["I_aug"]), p(dst["I1_aug"]),
                                      p(dst["I2_aug"]), p(dst["patch_indices"]), eng.B, eng.img_h, eng.img_w, eng.Pz,
                                      ctypes.c_void_p(cur.cuda_stream)), "udh_prep_inputs_u8")
-        out = eng.train_step(dst) if train else eng.forward(dst, train=False)
+        out = eng.train_step(dst) if train else eng.eval_step(dst)
         self.free[slot].record(cur)
         res = torch.cat([out["h4p_metrics"], out["photo_losses"]])
         self.host_results[slot].copy_(res, non_blocking=True)
