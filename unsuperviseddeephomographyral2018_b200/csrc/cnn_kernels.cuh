@@ -14,16 +14,6 @@ namespace udh {
 int conv3x3_simt(const float* in0, const float* in1, const float* w, const float* bias, const float* mask_src,
                  float* out, int B, int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
 
-// same convolution, output written as a zero-bordered bf16 stream [B,H+2,W+2,Cout] (interior only)
-int conv3x3_simt_bf16out(const float* in0, const float* in1, const float* w, const float* bias, __nv_bfloat16* out_pad, int B,
-                         int H, int W, int Cin, int Cout, int relu, cudaStream_t st);
-
-// conv1_1 (2 -> 64) of the bf16 mode: warp-per-row CUDA-core kernels on the bf16 padded streams (conv1_simt.cu)
-int conv1_fwd_bf16(const float* I1, const float* I2, const float* w, const float* bias, __nv_bfloat16* out_pad, uint32_t* mask_out,
-                   int B, int H, int W, cudaStream_t st);
-int conv1_wgrad_bf16(const float* I1, const float* I2, const __nv_bfloat16* G_pad, float* dW, float* db, int B, int H, int W,
-                     cudaStream_t st);
-
 // dW[ky,kx,ci,co] += sum_{n,y,x} x[n,y+ky-1,x+kx-1,ci] * g[n,y,x,co];  db[co] += sum g   (atomic accumulation)
 int wgrad3x3_simt(const float* x0, const float* x1, const float* g, float* dW, float* db, int B, int H, int W,
                   int Cin, int Cout, cudaStream_t st);

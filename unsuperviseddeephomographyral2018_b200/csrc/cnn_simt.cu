@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_halo(float* in_s, const float* __restrict__
 // ---------------------------------------------------------------------------------------------------------
 // conv 3x3, pad 1, stride 1: CTA = 8x16 output pixels x 64 output channels, thread = 8 pixels x 4 channels.
 // ---------------------------------------------------------------------------------------------------------
-template <int CK, bool TWO_PLANE, bool BF16_PAD_OUT = false>
+template <int CK, bool TWO_PLANE>
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       const float* __restrict__ mask_src, float* __restrict__ out, int H,
@@ -119,15 +119,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
       const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + o));
       v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
     }
-    if (BF16_PAD_OUT) {
-      __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
-      const size_t op = (((size_t)n * (H + 2) + y + 1) * (W + 2) + x0 + col0 + p + 1) * Cout + co0 + cg * 4;
-      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-      uint2 pk; pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(ob + op) = pk;
-    } else {
-      *reinterpret_cast<float4*>(out + o) = v;
-    }
+    *reinterpret_cast<float4*>(out + o) = v;
   }
 }
 
@@ -383,14 +375,6 @@ int conv3x3_simt(const float* in0, const float* in1, const float* w, const float
     conv3x3_kernel<8, false><<<grid, 256, 0, st>>>(in0, nullptr, w, bias, mask_src, out, H, W, Cin, Cout, relu);
   }
   return check_launch("conv3x3_simt");
-}
-
-int conv3x3_simt_bf16out(const float* in0, const float* in1, const float* w, const float* bias, __nv_bfloat16* out_pad, int B,
-                         int H, int W, int Cin, int Cout, int relu, cudaStream_t st) {
-  UDH_REQUIRE(in1 && Cin == 2 && H % TH == 0 && W % TW == 0 && Cout % 64 == 0, "conv3x3_simt_bf16out: only the two-plane first layer");
-  dim3 grid((H / TH) * (W / TW), B, Cout / 64);
-  conv3x3_kernel<2, true, true><<<grid, 256, 0, st>>>(in0, in1, w, bias, nullptr, reinterpret_cast<float*>(out_pad), H, W, Cin, Cout, relu);
-  return check_launch("conv3x3_simt_bf16out");
 }
 
 int wgrad3x3_simt(const float* x0, const float* x1, const float* g, float* dW, float* db, int B, int H, int W, int Cin,
