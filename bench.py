@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--loss_type", default="h_loss")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short BASELINE configs[2]/[3] side measurements")
     return ap.parse_args()
 
 
@@ -301,6 +302,9 @@ def run_ours(args):
                 roof["traffic"] = json.load(open(tr)).get(name.split(" ")[0])
             except Exception:
                 pass
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = other_configs(torch, _lib, engine, synthetic, numeric, peaks, dev)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sb = 8
@@ -317,10 +321,77 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         "tflops_algorithmic": TRAIN_FLOP_PER_PAIR * B * world / (ms_step * 1e-3) / 1e12,
         "phases_ms_per_step": {k: round(v[0] / K, 4) for k, v in sorted(phases.items(), key=lambda kv: -kv[1][0])},
+        "other_configs": extras,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs(torch, _lib, engine, synthetic, numeric, peaks, dev):
+    """Short side measurements of BASELINE configs[2] (inference CNN+DLT forward, B=512) and configs[3] (fused warp + L1 on
+    the full 320x240 grid, B=64) — reported next to the headline, not as the headline."""
+    import ctypes
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    try:
+        B3 = 512
+        eng = engine.HomographyEngine(B3, numeric=numeric, seed=0, device=dev)
+        b = synthetic.make_batch(B3, seed=77, device=dev)
+        h4p = torch.empty(B3, 8, device=dev); H = torch.empty(B3, 9, device=dev)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def fwd():
+            _lib.check(_lib.lib.udh_cnn_fwd(p(eng.params), p(b["I1_aug"]), p(b["I2_aug"]), p(h4p), p(eng.ws), eng.ws_bytes, B3, 128, 0, 0, eng.numeric, st), "cnn_fwd")
+            _lib.check(_lib.lib.udh_dlt_fwd(p(b["pts1"]), p(h4p), p(H), B3, st), "dlt")
+        for _ in range(3):
+            fwd()
+        e0, e1 = ev(), ev(); torch.cuda.synchronize(); e0.record()
+        n = 10
+        for _ in range(n):
+            fwd()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out["configs[2] inference CNN+DLT forward, B=512"] = {"pairs_per_s": B3 / (ms * 1e-3), "ms_per_batch": ms,
+                                                               "tflops_algorithmic": FWD_FLOP_PER_PAIR * B3 / (ms * 1e-3) / 1e12,
+                                                               "frac_of_bf16_peak": FWD_FLOP_PER_PAIR * B3 / (ms * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        del eng, b
+        torch.cuda.empty_cache()
+    except Exception as e:                                     # side measurement only
+        out["configs[2] error"] = repr(e)[:200]
+    try:
+        B4, Hh, W = 64, 240, 320
+        nb = 4                                                 # 4 x 39.3 MB of inputs rotate through the 126 MB L2
+        g = torch.Generator(device=dev).manual_seed(5)
+        src = [torch.randn(B4, Hh, W, 1, device=dev, generator=g) for _ in range(nb)]
+        tgt = [torch.randn(B4, Hh, W, 1, device=dev, generator=g) for _ in range(nb)]
+        pts = torch.tensor([[96., 56., 224., 56., 224., 184., 96., 184.]], device=dev).repeat(B4, 1).contiguous()
+        hh = (torch.rand(B4, 8, device=dev, generator=g) * 20 - 10).contiguous()
+        Hm = torch.empty(B4, 9, device=dev); sums = torch.zeros(8, device=dev, dtype=torch.float64)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib.udh_dlt_fwd(p(pts), p(hh), p(Hm), B4, st), "dlt")
+
+        def warp(i):
+            _lib.check(_lib.lib.udh_warp_loss_fwd(p(src[i % nb]), 1, Hh, W, p(Hm), p(tgt[i % nb]), None, 0, W, Hh, None, p(sums), B4, st), "warp")
+        for i in range(4):
+            warp(i)
+        e0, e1 = ev(), ev(); torch.cuda.synchronize(); e0.record()
+        n = 40
+        for i in range(n):
+            warp(i)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        byts = 614400.0 * B4
+        out["configs[3] fused warp+L1, full 320x240 grid, B=64"] = {
+            "pairs_per_s": B4 / (ms * 1e-3), "us_per_launch": ms * 1e3,
+            "roofline": {"bound": "hbm", "achieved": byts / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": byts / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": byts,
+                         "l2_policy": "4 rotating input sets of 39.3 MB (157 MB > 126 MB L2)"}}
+    except Exception as e:
+        out["configs[3] error"] = repr(e)[:200]
+    return out
 
 
 def _bf16_available(_lib):

@@ -84,3 +84,20 @@ def test_data_parallel_contract_gloo_world2(tmp_path):
                         "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_named_checkpoint_roundtrip(tmp_path):
+    """TF-Slim variable names / shapes: export -> import is lossless, wrong shapes are rejected."""
+    from unsuperviseddeephomographyral2018_b200 import params as P
+    flat = P.init_flat(3)
+    path = str(tmp_path / "ckpt.npz")
+    P.save_named_npz(path, flat, extra={"global_step": np.array(1234)})
+    z = np.load(path)
+    assert z["model/conv_block1/conv1/weights"].shape == (3, 3, 2, 64) and z["model/fc1/fc1/weights"].shape == (32768, 1024)
+    assert z["model/fc2/fc2/biases"].shape == (8,) and int(z["global_step"]) == 1234
+    back = P.load_named_npz(path)
+    assert np.array_equal(back, flat)
+    bad = dict(z); bad["model/fc2/fc2/weights"] = np.zeros((8, 1024), np.float32)
+    np.savez(str(tmp_path / "bad.npz"), **bad)
+    with pytest.raises(ValueError):
+        P.load_named_npz(str(tmp_path / "bad.npz"))

@@ -81,6 +81,14 @@ class HomographyEngine(object):
     def named_gradients(self):
         return P.unflatten(self.grads, self.specs)
 
+    def export_named(self, path):
+        """Parameters under the reference's TF-Slim variable names / shapes (+ global_step)."""
+        import numpy as np
+        P.save_named_npz(path, self.params.cpu().numpy(), extra={"global_step": np.array(self.global_step)})
+
+    def import_named(self, path):
+        self.load_flat(P.load_named_npz(path, self.Pz))
+
     def state_dict(self):
         return OrderedDict(params=self.params.cpu(), adam_m=self.adam_m.cpu(), adam_v=self.adam_v.cpu(),
                            global_step=self.global_step, patch_size=self.Pz)

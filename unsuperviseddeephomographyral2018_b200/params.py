@@ -82,3 +82,28 @@ def unflatten(flat, specs=None):
     """Views (no copy) of a flat numpy / torch buffer, keyed by checkpoint name."""
     specs = specs or param_specs()
     return OrderedDict((n, flat[s.offset:s.offset + s.size].reshape(s.shape)) for n, s in specs.items())
+
+
+def save_named_npz(path, flat, extra=None):
+    """Write the parameters under the reference's TF-Slim variable names and shapes: a TF-1 checkpoint
+    converts to / from this file with `{v.name[:-2]: sess.run(v) for v in tf.global_variables()}`."""
+    flat = np.asarray(flat, dtype=np.float32)
+    arrays = {n: np.array(v) for n, v in unflatten(flat).items()}
+    if extra:
+        arrays.update(extra)
+    np.savez(path, **arrays)
+
+
+def load_named_npz(path, patch_size=128):
+    """Inverse of save_named_npz: flat fp32 buffer in this package's layout (shapes are checked)."""
+    specs = param_specs(patch_size)
+    flat = np.zeros(total_floats(specs), dtype=np.float32)
+    with np.load(path) as z:
+        for n, s in specs.items():
+            if n not in z:
+                raise KeyError("checkpoint is missing variable %s" % n)
+            a = np.asarray(z[n], dtype=np.float32)
+            if tuple(a.shape) != s.shape:
+                raise ValueError("variable %s has shape %s, expected %s" % (n, a.shape, s.shape))
+            flat[s.offset:s.offset + s.size] = a.reshape(-1)
+    return flat
