@@ -356,7 +356,7 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   kern<<<dim3(gx, gy), 256, smem, st>>>(tmX128, tmXhh, tmG, g, dW, CBX == 1 ? db : nullptr);
   TRY(check_launch("tc_wgrad_kernel"));
   if (CBX == 2 && db) {
-    colsum_bf16_kernel<<<296, 256, 0, st>>>(gsrc, db, g.Q, N_OUT);
+    colsum_bf16_kernel<<<148 * 8, 256, 0, st>>>(gsrc, db, g.Q, N_OUT);
     TRY(check_launch("colsum_bf16"));
   }
   return UDH_OK;
