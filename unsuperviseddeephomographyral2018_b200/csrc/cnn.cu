@@ -74,6 +74,8 @@ int check_cnn_args(const char* fn, int B, int P, int numeric_mode) {
   UDH_REQUIRE(P >= 128 && P % 128 == 0, "%s: patch size must be a multiple of 128 (got %d)", fn, P);
   UDH_REQUIRE(numeric_mode == UDH_NUMERIC_FP32 || numeric_mode == UDH_NUMERIC_BF16, "%s: unknown numeric_mode %d", fn,
               numeric_mode);
+  UDH_REQUIRE(numeric_mode != UDH_NUMERIC_BF16 || P == 128,
+              "%s: UDH_NUMERIC_BF16 is tiled for the reference's 128x128 patches (got %d); use UDH_NUMERIC_FP32", fn, P);
   return UDH_OK;
 }
 
@@ -100,6 +102,7 @@ extern "C" int udh_param_offset(int P, int tensor, size_t* offset_floats, size_t
 
 extern "C" size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode) {
   if (B < 1 || P < 128 || P % 128) return 0;
+  if (numeric_mode == UDH_NUMERIC_BF16 && P != 128) return 0;
   return Workspace(B, P, numeric_mode).total;
 }
 

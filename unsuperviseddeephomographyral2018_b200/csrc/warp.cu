@@ -117,8 +117,40 @@ __device__ __forceinline__ void window_origin(const int32_t* __restrict__ patch_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// forward: grid (ceil(pw/128) * ceil(ph/8), B), 256 threads; each thread owns 4 consecutive output pixels.
+// forward: grid (ceil(pw/128) * ceil(ph/32), B), 256 threads; each thread owns 4 consecutive pixels of 4 rows
+// (rows interleaved by 8 so a warp still walks whole 128-pixel row segments: coalesced float4 I2 / pred accesses).
+// In-range samples (the common case) take a branch-free fast path that produces bit-identical weights; samples whose
+// taps clip go through the general reference-exact path.  Reductions: fp32 over the thread's 16 pixels, then fp64.
 // ------------------------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ float sample_pixel(const float* __restrict__ img, const Homog& hm, float xt, float yt, float bx, float by,
+                                              float bt, int W, int Hh) {
+  const float xs = fmaf(hm.h[0], xt, bx), ys = fmaf(hm.h[3], xt, by);
+  float ts = fmaf(hm.h[6], xt, bt);
+  if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;
+  const float x = (xs / ts + 1.0f) * (float)W / 2.0f;
+  const float y = (ys / ts + 1.0f) * (float)Hh / 2.0f;
+  if (x >= 0.0f && x < (float)(W - 1) && y >= 0.0f && y < (float)(Hh - 1)) {
+    // no tap clips: floor == truncation, x1 = x0 + 1 — same fp32 values as the general path
+    const int x0 = (int)x, y0 = (int)y;
+    const float x0f = (float)x0, y0f = (float)y0;
+    const float dx1 = (x0f + 1.0f) - x, dx0 = x - x0f, dy1 = (y0f + 1.0f) - y, dy0 = y - y0f;
+    const float wa = __fmul_rn(dx1, dy1), wb = __fmul_rn(dx1, dy0), wc = __fmul_rn(dx0, dy1), wd = __fmul_rn(dx0, dy0);
+    const float* p0 = img + ((size_t)y0 * W + x0) * C;
+    const float* p1 = p0 + (size_t)W * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float Ia = __ldg(p0 + c), Ic = __ldg(p0 + C + c), Ib = __ldg(p1 + c), Id = __ldg(p1 + C + c);
+      acc = __fadd_rn(acc, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)), __fmul_rn(wd, Id)));
+    }
+    return C == 1 ? acc : acc / (float)C;
+  }
+  Tap t;
+  sample_setup(hm, xt, yt, W, Hh, t);
+  return sample_gray<C>(img, t);
+}
+
 template <int C>
 __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restrict__ I, int img_h, int img_w,
                                                             const float* __restrict__ H, const float* __restrict__ I2,
@@ -130,7 +162,6 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
   const int tiles_x = (pw + 127) >> 7;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
   const int c0 = (tx << 7) + ((threadIdx.x & 31) << 2);
-  const int r = (ty << 3) + (threadIdx.x >> 5);
   Homog hm;
   normalise_h(H + (size_t)b * 9, img_w, img_h, hm);
   hm.step_x = 2.0f / (float)(img_w - 1);                     // TF LinSpace: step = (stop-start)/(num-1)
@@ -139,37 +170,42 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
   window_origin(patch_indices, idx_stride, b, img_w, ox, oy);
   const float* img = I + (size_t)b * img_h * img_w * C;
 
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  if (r < ph && c0 < pw) {
-    const float yt = fmaf(hm.step_y, (float)(oy + r), -1.0f);
-    float p[4];
+  float s_abs = 0.f, s_sq = 0.f, s_hub = 0.f, s_xy = 0.f, s_xx = 0.f, s_yy = 0.f;
+  if (c0 < pw) {
+    float xt[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float xt = fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f);
-      Tap t;
-      sample_setup(hm, xt, yt, img_w, img_h, t);
-      p[k] = sample_gray<C>(img, t);
-    }
-    const size_t o = ((size_t)b * ph + r) * pw + c0;
-    if (pred) *reinterpret_cast<float4*>(pred + o) = make_float4(p[0], p[1], p[2], p[3]);
-    if (I2) {
-      const float4 tv = __ldg(reinterpret_cast<const float4*>(I2 + o));
-      const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
-      float s_abs = 0.f, s_sq = 0.f, s_hub = 0.f, s_xy = 0.f, s_xx = 0.f, s_yy = 0.f;
+    for (int k = 0; k < 4; ++k) xt[k] = fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float d = p[k] - tg[k], ad = fabsf(d);
-        s_abs += ad;
-        s_sq = fmaf(d, d, s_sq);
-        s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-        s_xy = fmaf(p[k], tg[k], s_xy);
-        s_xx = fmaf(p[k], p[k], s_xx);
-        s_yy = fmaf(tg[k], tg[k], s_yy);
+    for (int i = 0; i < 4; ++i) {
+      const int r = (ty << 5) + (i << 3) + (threadIdx.x >> 5);
+      if (r < ph) {
+        const float yt = fmaf(hm.step_y, (float)(oy + r), -1.0f);
+        // row-constant parts of T_g = H' . (x_t, y_t, 1): identical to fmaf(h0, xt, fmaf(h1, yt, h2)) etc.
+        const float bx = fmaf(hm.h[1], yt, hm.h[2]), by = fmaf(hm.h[4], yt, hm.h[5]), bt = fmaf(hm.h[7], yt, hm.h[8]);
+        float p[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] = sample_pixel<C>(img, hm, xt[k], yt, bx, by, bt, img_w, img_h);
+        const size_t o = ((size_t)b * ph + r) * pw + c0;
+        if (pred) *reinterpret_cast<float4*>(pred + o) = make_float4(p[0], p[1], p[2], p[3]);
+        if (I2) {
+          const float4 tv = __ldg(reinterpret_cast<const float4*>(I2 + o));
+          const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float d = p[k] - tg[k], ad = fabsf(d);
+            s_abs += ad;
+            s_sq = fmaf(d, d, s_sq);
+            s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+            s_xy = fmaf(p[k], tg[k], s_xy);
+            s_xx = fmaf(p[k], p[k], s_xx);
+            s_yy = fmaf(tg[k], tg[k], s_yy);
+          }
+        }
       }
-      acc[0] = s_abs; acc[1] = s_sq; acc[2] = s_hub; acc[3] = s_xy; acc[4] = s_xx; acc[5] = s_yy;
     }
   }
   if (sums && I2) {
+    double acc[6] = {s_abs, s_sq, s_hub, s_xy, s_xx, s_yy};
     block_sum<double, 6>(acc, red);
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -355,7 +391,7 @@ extern "C" int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, co
   if (rc) return rc;
   UDH_REQUIRE(pred || (I2 && sums), "udh_warp_loss_fwd: nothing to compute (no pred, no I2+sums)");
   if (B == 0) return UDH_OK;
-  dim3 grid(((pw + 127) / 128) * ((ph + 7) / 8), B);
+  dim3 grid(((pw + 127) / 128) * ((ph + 31) / 32), B);
   ProfScope ps(PROF_WARP_FWD, as_stream(stream));
   if (C == 3)
     warp_loss_fwd_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
