@@ -40,6 +40,8 @@ extern "C" {
 #define UDH_LOSS_L1 0        /* homography_model.py:328 */
 #define UDH_LOSS_REC 1       /* homography_model.py:303 */
 #define UDH_LOSS_L1_SMOOTH 2 /* homography_model.py:136-139,340 */
+#define UDH_LOSS_NCC 3       /* homography_model.py:161-166,351 */
+#define UDH_LOSS_CUSTOM 4    /* per-pixel d loss / d pred supplied by the caller (ssim_loss: udh_ssim_bwd) */
 
 /* slots of the `sums` accumulator (double[UDH_NSUMS]) filled by udh_warp_loss_fwd / udh_ssim_fwd */
 #define UDH_SUM_ABS 0   /* sum |pred - I2|            */
@@ -95,6 +97,12 @@ int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, const float* 
 int udh_warp_loss_bwd(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
                       const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, int loss_type,
                       const double* sums, float upstream, float* dH, float* scratch, int B, void* stream);
+/* same, with the per-pixel upstream gradient dpred[B,ph,pw] for UDH_LOSS_CUSTOM (NULL otherwise) */
+int udh_warp_loss_bwd_ex(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                         const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, int loss_type,
+                         const double* sums, const float* dpred, float upstream, float* dH, float* scratch, int B, void* stream);
+/* d mean(clip((1-SSIM)/2,0,1)) / d pred -> dpred[B,ph,pw] (homography_model.py:141-158,316); feed to udh_warp_loss_bwd_ex. */
+int udh_ssim_bwd(const float* pred, const float* I2, int pw, int ph, float* dpred, int B, void* stream);
 /* SSIM diagnostic (homography_model.py:141-158): adds sum over the VALID 3x3 grid into sums[UDH_SUM_SSIM]. */
 int udh_ssim_fwd(const float* pred, const float* I2, int pw, int ph, double* sums, int B, void* stream);
 /* losses[UDH_NLOSSES] from sums; n = B*ph*pw, n_ssim = B*(ph-2)*(pw-2). */
@@ -164,6 +172,8 @@ int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_
 #define UDH_STEP_LOSS_L1 1
 #define UDH_STEP_LOSS_REC 2
 #define UDH_STEP_LOSS_L1_SMOOTH 3
+#define UDH_STEP_LOSS_NCC 4
+#define UDH_STEP_LOSS_SSIM 5
 typedef struct {
   int B, P, img_h, img_w, C;      /* batch, patch size, image size, channels of I_aug (1 or 3) */
   int numeric_mode, loss_type, train;
@@ -173,6 +183,7 @@ typedef struct {
   const int32_t* patch_indices; int64_t idx_stride;
   float *h4p, *H, *pred_I2;       /* [B,8], [B,9], [B,P,P] (pred_I2 may be NULL: then no SSIM) */
   float *dh4p, *dH, *scratch;     /* [B,8], [B,9], [B,9] */
+  float* dpred_map;               /* [B,P,P] scratch, only for UDH_STEP_LOSS_SSIM */
   double* sums;                   /* [UDH_NSUMS] */
   float *photo_losses, *h4p_metrics, *per_sample;   /* [UDH_NLOSSES], [UDH_NMETRICS], [B] or NULL */
 } udh_step_args;

@@ -180,7 +180,7 @@ def test_warp_gray_input_and_full_grid(udh):
     assert abs(l1 - ref_l1) <= 1e-4 * ref_l1
 
 
-@pytest.mark.parametrize("loss_name", ["l1_loss", "rec_loss", "l1_smooth_loss"])
+@pytest.mark.parametrize("loss_name", ["l1_loss", "rec_loss", "l1_smooth_loss", "ncc_loss", "ssim_loss"])
 def test_warp_loss_backward_vs_fp64_autograd(udh, loss_name):
     B = 3
     batch = O.make_batch(21, B, dtype=torch.float64)
@@ -188,11 +188,17 @@ def test_warp_loss_backward_vs_fp64_autograd(udh, loss_name):
     H = O.solve_dlt(batch["pts1"], h4p).detach().requires_grad_(True)
     pred = O.transform(batch["I_aug"], H, batch["patch_indices"], 128)
     O.losses(h4p, None, pred, batch["I2_aug"])[loss_name].backward()
-    lt = {"l1_loss": udh.lib.LOSS_L1, "rec_loss": udh.lib.LOSS_REC, "l1_smooth_loss": udh.lib.LOSS_L1_SMOOTH}[loss_name]
+    lt = {"l1_loss": udh.lib.LOSS_L1, "rec_loss": udh.lib.LOSS_REC, "l1_smooth_loss": udh.lib.LOSS_L1_SMOOTH, "ncc_loss": udh.lib.LOSS_NCC,
+          "ssim_loss": udh.lib.LOSS_CUSTOM}[loss_name]
     b = dev({k: (v.float() if isinstance(v, torch.Tensor) and v.dtype == torch.float64 else v) for k, v in batch.items()})
     Hc = H.detach().float().cuda().contiguous()
-    _, sums = udh.ops.warp_loss_forward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, want_pred=False)
-    dH = udh.ops.warp_loss_backward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, lt, sums).cpu().double()
+    predc, sums = udh.ops.warp_loss_forward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, want_pred=True)
+    dpm = udh.ops.ssim_backward(predc, b["I2_aug"], 128, 128) if loss_name == "ssim_loss" else None
+    if dpm is not None:                                                     # the per-pixel SSIM gradient itself vs fp64 autograd
+        pr = pred.detach().clone().requires_grad_(True)
+        O.ssim_map(pr, batch["I2_aug"]).mean().backward()
+        assert rel_l2(dpm.cpu().double().reshape(-1), pr.grad.reshape(-1)) < 2e-3
+    dH = udh.ops.warp_loss_backward(b["I_aug"], Hc, b["I2_aug"], b["patch_indices"], 128, 128, lt, sums, dpred=dpm).cpu().double()
     g = H.grad.clone(); g[:, 2, 2] = 0; dH[:, 2, 2] = 0                     # h33 is a constant downstream
     for i in range(B):
         assert rel_l2(dH[i], g[i]) < 5e-3, (i, dH[i], g[i])
@@ -369,7 +375,7 @@ def test_device_input_pipeline_and_synthetic_generator(udh):
 
 def test_one_call_step_equals_separate_calls(udh):
     """udh_step_forward_backward (one C call per step) == forward() + backward() through the individual entry points."""
-    for loss_type in ("h_loss", "l1_loss"):
+    for loss_type in ("h_loss", "l1_loss", "ssim_loss", "ncc_loss", "rec_loss", "l1_smooth_loss"):
         batch = dev(O.make_batch(2, 3))
         e1 = udh.engine.HomographyEngine(3, seed=1, loss_type=loss_type, lr=5e-4)
         e2 = udh.engine.HomographyEngine(3, seed=1, loss_type=loss_type, lr=5e-4)
@@ -378,6 +384,9 @@ def test_one_call_step_equals_separate_calls(udh):
         assert (o1["pred_h4p"] - o2["pred_h4p"]).abs().max().item() < 1e-6
         for k in d1:
             assert abs(d1[k] - d2[k]) <= 1e-5 * max(1.0, abs(d1[k])), k
-        assert (e1.params - e2.params).abs().max().item() <= 1e-6 and e2.global_step == 1
+        # TF-Adam's first step is ~lr*sign(g): compare where g is not rounding noise (fp32 atomics reorder between runs)
+        big = g1.abs() > 1e-3 * g1.abs().max()
+        assert (e1.params - e2.params)[big].abs().max().item() <= 0.02 * 5e-4 and e2.global_step == 1
+        assert rel_l2(e2.adam_m.cpu(), e1.adam_m.cpu()) < 1e-4
         ev = e2.losses_dict(e2.eval_step(batch))
         assert abs(ev["l1_loss"] - e2.losses_dict(e2.forward(batch, train=False))["l1_loss"]) < 1e-6

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libudh.so")
 OK, EINVAL, ECUDA, ENOSUP, EWS = 0, -1, -2, -3, -4
 NUMERIC_FP32, NUMERIC_BF16 = 0, 1
 BWD_ALL, BWD_HEAD, BWD_CONVS = 0, 1, 2
-LOSS_L1, LOSS_REC, LOSS_L1_SMOOTH = 0, 1, 2
+LOSS_L1, LOSS_REC, LOSS_L1_SMOOTH, LOSS_NCC, LOSS_CUSTOM = 0, 1, 2, 3, 4
 NSUMS, NLOSSES, NMETRICS = 8, 8, 4
 L_REC, L_SSIM, L_L1, L_L1_SMOOTH, L_NCC = 0, 1, 2, 3, 4
 M_H_LOSS, M_BOUNDED_H_LOSS, M_NUM_FAIL, M_ACE = 0, 1, 2, 3
@@ -25,12 +25,12 @@ class StepArgs(ctypes.Structure):
                 ("I1", c_void_p), ("I2", c_void_p), ("I_aug", c_void_p), ("pts1", c_void_p), ("gt", c_void_p),
                 ("patch_indices", c_void_p), ("idx_stride", c_int64),
                 ("h4p", c_void_p), ("H", c_void_p), ("pred_I2", c_void_p),
-                ("dh4p", c_void_p), ("dH", c_void_p), ("scratch", c_void_p), ("sums", c_void_p),
+                ("dh4p", c_void_p), ("dH", c_void_p), ("scratch", c_void_p), ("dpred_map", c_void_p), ("sums", c_void_p),
                 ("photo_losses", c_void_p), ("h4p_metrics", c_void_p), ("per_sample", c_void_p)]
 
 
 STEP_ALL, STEP_FWD_HEAD, STEP_CONVS, STEP_FWD_ONLY = 0, 1, 2, 3
-STEP_LOSS = {"h_loss": 0, "l1_loss": 1, "rec_loss": 2, "l1_smooth_loss": 3}
+STEP_LOSS = {"h_loss": 0, "l1_loss": 1, "rec_loss": 2, "l1_smooth_loss": 3, "ncc_loss": 4, "ssim_loss": 5}
 
 
 # name -> (restype, argtypes); every symbol include/udh.h declares
@@ -44,6 +44,9 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_int, c_void_p]),
     "udh_warp_loss_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                   c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_warp_loss_bwd_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "udh_ssim_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "udh_ssim_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "udh_photo_losses_finalize": (c_int, [c_void_p, c_double, c_double, c_void_p, c_void_p]),
     "udh_transformer_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -29,9 +29,21 @@ extern "C" int udh_step_forward_backward(const udh_step_args* a, int phase, void
     UDH_REQUIRE(a->grads && a->dh4p, "udh_step_forward_backward: backward needs grads and dh4p buffers");
     if (a->loss_type != UDH_STEP_LOSS_H) {
       UDH_REQUIRE(a->dH && a->scratch, "udh_step_forward_backward: photometric backward needs dH and scratch");
-      const int lt = a->loss_type == UDH_STEP_LOSS_L1 ? UDH_LOSS_L1 : a->loss_type == UDH_STEP_LOSS_REC ? UDH_LOSS_REC : UDH_LOSS_L1_SMOOTH;
-      STEP_TRY(udh_warp_loss_bwd(a->I_aug, a->C, a->img_h, a->img_w, a->H, a->I2, a->patch_indices, a->idx_stride, P, P, lt, a->sums,
-                                 1.0f, a->dH, a->scratch, B, stream));
+      int lt;
+      switch (a->loss_type) {
+        case UDH_STEP_LOSS_L1: lt = UDH_LOSS_L1; break;
+        case UDH_STEP_LOSS_REC: lt = UDH_LOSS_REC; break;
+        case UDH_STEP_LOSS_L1_SMOOTH: lt = UDH_LOSS_L1_SMOOTH; break;
+        case UDH_STEP_LOSS_NCC: lt = UDH_LOSS_NCC; break;
+        case UDH_STEP_LOSS_SSIM: lt = UDH_LOSS_CUSTOM; break;
+        default: udh::set_error("udh_step_forward_backward: unknown loss_type %d", a->loss_type); return UDH_EINVAL;
+      }
+      if (lt == UDH_LOSS_CUSTOM) {
+        UDH_REQUIRE(a->pred_I2 && a->dpred_map, "udh_step_forward_backward: ssim_loss needs pred_I2 and dpred_map");
+        STEP_TRY(udh_ssim_bwd(a->pred_I2, a->I2, P, P, a->dpred_map, B, stream));
+      }
+      STEP_TRY(udh_warp_loss_bwd_ex(a->I_aug, a->C, a->img_h, a->img_w, a->H, a->I2, a->patch_indices, a->idx_stride, P, P, lt, a->sums,
+                                    lt == UDH_LOSS_CUSTOM ? a->dpred_map : nullptr, 1.0f, a->dH, a->scratch, B, stream));
       STEP_TRY(udh_dlt_bwd(a->pts1, a->h4p, a->H, a->dH, a->dh4p, B, stream));
     } else {
       UDH_REQUIRE(a->gt, "udh_step_forward_backward: h_loss needs gt");

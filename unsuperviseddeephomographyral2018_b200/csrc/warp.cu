@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(256) warp_loss_bwd_kernel(const float* __restr
                                                             const float* __restrict__ H, const float* __restrict__ I2,
                                                             const int32_t* __restrict__ patch_indices, int64_t idx_stride,
                                                             int pw, int ph, int loss_type, const double* __restrict__ sums,
-                                                            float upstream, double n_total, float* __restrict__ dHn) {
+                                                            const float* __restrict__ dpred, float upstream, double n_total,
+                                                            float* __restrict__ dHn) {
   __shared__ float red[9 * 32];
   const int b = blockIdx.y;
   const int tiles_x = (pw + 127) >> 7;
@@ -238,8 +239,17 @@ __global__ void __launch_bounds__(256) warp_loss_bwd_kernel(const float* __restr
   const float* img = I + (size_t)b * img_h * img_w * C;
 
   // d loss / d pred = coef * f(d):  L1: sign(d)/N;  REC: d/(N*rec);  L1_SMOOTH: clamp(d,-1,1)/N
+  //   NCC (homography_model.py:161-166): ncc = sqrt(2 - 2c), c = <p,t>/(|p||t|):  d ncc/d p_i = -(t_i/(|p||t|) - c p_i/|p|^2)/ncc
+  //   CUSTOM: d loss / d pred is given per pixel (used for ssim_loss, whose 3x3 windows couple neighbouring pixels)
   float coef = upstream / (float)n_total;
+  float ncc_a = 0.f, ncc_b = 0.f;
   if (loss_type == UDH_LOSS_REC) coef = upstream / (float)(n_total * sqrt(sums[UDH_SUM_SQ] / n_total));
+  if (loss_type == UDH_LOSS_NCC) {
+    const double pp = sums[UDH_SUM_XX], tt = sums[UDH_SUM_YY], c = sums[UDH_SUM_XY] / sqrt(pp * tt);
+    const double ncc = sqrt(fmax(1e-30, 2.0 - 2.0 * c));
+    ncc_a = (float)(-(double)upstream / (ncc * sqrt(pp * tt)));
+    ncc_b = (float)((double)upstream * c / (ncc * pp));
+  }
 
   float g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (r < ph && c0 < pw) {
@@ -252,11 +262,14 @@ __global__ void __launch_bounds__(256) warp_loss_bwd_kernel(const float* __restr
       const float xt = fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f);
       Tap t;
       sample_setup(hm, xt, yt, img_w, img_h, t);
-      const float d = sample_gray<C>(img, t) - tg[k];
+      const float pv = sample_gray<C>(img, t);
+      const float d = pv - tg[k];
       float gp;
       if (loss_type == UDH_LOSS_L1) gp = (d > 0.f) ? coef : ((d < 0.f) ? -coef : 0.f);
       else if (loss_type == UDH_LOSS_REC) gp = coef * d;
-      else gp = coef * fminf(fmaxf(d, -1.0f), 1.0f);
+      else if (loss_type == UDH_LOSS_L1_SMOOTH) gp = coef * fminf(fmaxf(d, -1.0f), 1.0f);
+      else if (loss_type == UDH_LOSS_NCC) gp = fmaf(ncc_a, tg[k], ncc_b * pv);
+      else gp = upstream * __ldg(dpred + o + k);
       float gx, gy;
       sample_grad<C>(img, t, gx, gy);
       const float Gx = gp * gx * (0.5f * (float)img_w);      // through x = (xn+1)*W/2
@@ -334,6 +347,43 @@ __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ X, 
   if (threadIdx.x == 0) atomicAdd(sums + UDH_SUM_SSIM, acc[0]);
 }
 
+// d mean(clip((1-SSIM)/2,0,1)) / d pred, one thread per pixel: every 3x3 window containing the pixel is re-evaluated.
+__global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Y, int pw, int ph,
+                                                       float inv_n, float* __restrict__ dX) {
+  const int b = blockIdx.y;
+  const float* x = X + (size_t)b * pw * ph;
+  const float* y = Y + (size_t)b * pw * ph;
+  const int ow = pw - 2, oh = ph - 2;
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f, k = 1.0f / 9.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pw * ph; i += gridDim.x * blockDim.x) {
+    const int r = i / pw, c = i - r * pw;
+    const float xi = x[i], yi = y[i];
+    float g = 0.f;
+    for (int wy = max(0, r - 2); wy <= min(oh - 1, r); ++wy)
+      for (int wx = max(0, c - 2); wx <= min(ow - 1, c); ++wx) {
+        float sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float a = __ldg(x + (wy + dy) * pw + wx + dx), bb = __ldg(y + (wy + dy) * pw + wx + dx);
+            sx += a; sy += bb; sxx = fmaf(a, a, sxx); syy = fmaf(bb, bb, syy); sxy = fmaf(a, bb, sxy);
+          }
+        const float mu_x = sx * k, mu_y = sy * k;
+        const float sig_x = sxx * k - mu_x * mu_x, sig_y = syy * k - mu_y * mu_y, sig_xy = sxy * k - mu_x * mu_y;
+        const float A1 = 2.f * mu_x * mu_y + C1, A2 = 2.f * sig_xy + C2, B1 = mu_x * mu_x + mu_y * mu_y + C1, B2 = sig_x + sig_y + C2;
+        const float S = (A1 * A2) / (B1 * B2);
+        const float L = (1.0f - S) * 0.5f;
+        if (L > 0.f && L < 1.f) {                             // inside the clip: dL/dS = -1/2
+          const float dA1 = 2.f * mu_y * k, dA2 = 2.f * (yi - mu_y) * k, dB1 = 2.f * mu_x * k, dB2 = 2.f * (xi - mu_x) * k;
+          const float dS = (dA1 * A2 + A1 * dA2) / (B1 * B2) - S * (dB1 * B2 + B1 * dB2) / (B1 * B2);
+          g += -0.5f * dS;
+        }
+      }
+    dX[(size_t)b * pw * ph + i] = g * inv_n;
+  }
+}
+
 __global__ void photo_finalize_kernel(const double* __restrict__ sums, double n, double n_ssim, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   out[UDH_L_REC] = (float)sqrt(sums[UDH_SUM_SQ] / n);
@@ -406,9 +456,20 @@ extern "C" int udh_warp_loss_bwd(const float* I, int C, int img_h, int img_w, co
   int rc = check_warp_args("udh_warp_loss_bwd", I, C, img_h, img_w, H, pw, ph, B);
   if (rc) return rc;
   UDH_REQUIRE(I2 && dH && scratch, "udh_warp_loss_bwd: null pointer");
-  UDH_REQUIRE(loss_type == UDH_LOSS_L1 || loss_type == UDH_LOSS_REC || loss_type == UDH_LOSS_L1_SMOOTH,
-              "udh_warp_loss_bwd: unsupported loss_type %d", loss_type);
-  UDH_REQUIRE(loss_type != UDH_LOSS_REC || sums, "udh_warp_loss_bwd: REC needs the forward sums");
+  return udh_warp_loss_bwd_ex(I, C, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, loss_type, sums, nullptr, upstream, dH, scratch,
+                              B, stream);
+}
+
+extern "C" int udh_warp_loss_bwd_ex(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                                    const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, int loss_type,
+                                    const double* sums, const float* dpred, float upstream, float* dH, float* scratch, int B,
+                                    void* stream) {
+  int rc = check_warp_args("udh_warp_loss_bwd", I, C, img_h, img_w, H, pw, ph, B);
+  if (rc) return rc;
+  UDH_REQUIRE(I2 && dH && scratch, "udh_warp_loss_bwd: null pointer");
+  UDH_REQUIRE(loss_type >= UDH_LOSS_L1 && loss_type <= UDH_LOSS_CUSTOM, "udh_warp_loss_bwd: unsupported loss_type %d", loss_type);
+  UDH_REQUIRE((loss_type != UDH_LOSS_REC && loss_type != UDH_LOSS_NCC) || sums, "udh_warp_loss_bwd: REC / NCC need the forward sums");
+  UDH_REQUIRE(loss_type != UDH_LOSS_CUSTOM || dpred, "udh_warp_loss_bwd: CUSTOM needs the per-pixel d loss / d pred");
   if (B == 0) return UDH_OK;
   cudaStream_t st = as_stream(stream);
   ProfScope ps(PROF_WARP_BWD, st);
@@ -416,9 +477,9 @@ extern "C" int udh_warp_loss_bwd(const float* I, int C, int img_h, int img_w, co
   dim3 grid(((pw + 127) / 128) * ((ph + 7) / 8), B);
   const double n_total = (double)B * pw * ph;
   if (C == 3)
-    warp_loss_bwd_kernel<3><<<grid, 256, 0, st>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, loss_type, sums, upstream, n_total, scratch);
+    warp_loss_bwd_kernel<3><<<grid, 256, 0, st>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, loss_type, sums, dpred, upstream, n_total, scratch);
   else
-    warp_loss_bwd_kernel<1><<<grid, 256, 0, st>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, loss_type, sums, upstream, n_total, scratch);
+    warp_loss_bwd_kernel<1><<<grid, 256, 0, st>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, loss_type, sums, dpred, upstream, n_total, scratch);
   rc = check_launch("udh_warp_loss_bwd");
   if (rc) return rc;
   conj_bwd_kernel<<<(B + 127) / 128, 128, 0, st>>>(scratch, dH, img_w, img_h, B);
@@ -434,6 +495,17 @@ extern "C" int udh_ssim_fwd(const float* pred, const float* I2, int pw, int ph, 
   ProfScope ps(PROF_SSIM, as_stream(stream));
   ssim_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, I2, pw, ph, sums);
   return check_launch("udh_ssim_fwd");
+}
+
+extern "C" int udh_ssim_bwd(const float* pred, const float* I2, int pw, int ph, float* dpred, int B, void* stream) {
+  UDH_REQUIRE(pred && I2 && dpred, "udh_ssim_bwd: null pointer");
+  UDH_REQUIRE(pw >= 3 && ph >= 3 && B >= 0, "udh_ssim_bwd: bad dimensions");
+  if (B == 0) return UDH_OK;
+  ProfScope ps(PROF_SSIM, as_stream(stream));
+  const float inv_n = 1.0f / ((float)B * (float)(pw - 2) * (float)(ph - 2));
+  dim3 grid(min((pw * ph + 255) / 256, 64), B);
+  ssim_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, I2, pw, ph, inv_n, dpred);
+  return check_launch("udh_ssim_bwd");
 }
 
 extern "C" int udh_photo_losses_finalize(const double* sums, double n, double n_ssim, float* losses, void* stream) {

@@ -16,7 +16,8 @@ from . import _lib, ops, params as P
 from ._lib import check, lib
 
 LOSS_TYPES = ("h_loss", "rec_loss", "ssim_loss", "l1_loss", "l1_smooth_loss", "ncc_loss")
-_PHOTO_BWD = {"l1_loss": _lib.LOSS_L1, "rec_loss": _lib.LOSS_REC, "l1_smooth_loss": _lib.LOSS_L1_SMOOTH}
+_PHOTO_BWD = {"l1_loss": _lib.LOSS_L1, "rec_loss": _lib.LOSS_REC, "l1_smooth_loss": _lib.LOSS_L1_SMOOTH, "ncc_loss": _lib.LOSS_NCC,
+              "ssim_loss": _lib.LOSS_CUSTOM}
 NUMERIC = {"fp32": _lib.NUMERIC_FP32, "bf16": _lib.NUMERIC_BF16}
 
 
@@ -148,11 +149,12 @@ class HomographyEngine(object):
             if dpred is None:
                 raise _lib.UdhError("h_loss needs gt")
         elif lt in _PHOTO_BWD:
+            dpm = ops.ssim_backward(out["pred_I2"], batch["I2_aug"], self.Pz, self.Pz) if lt == "ssim_loss" else None
             dH = ops.warp_loss_backward(batch["I_aug"], out["H_mat"], batch["I2_aug"], batch.get("patch_indices"), self.Pz,
-                                        self.Pz, _PHOTO_BWD[lt], out["_sums"], 1.0)
+                                        self.Pz, _PHOTO_BWD[lt], out["_sums"], 1.0, dpred=dpm)
             dpred = ops.dlt_backward(batch["pts1"], out["pred_h4p"], out["H_mat"], dH)
         else:
-            raise _lib.UdhError("loss_type %s has no CUDA backward yet (SURVEY §8f item 3)" % lt)
+            raise _lib.UdhError("unknown loss_type %s" % lt)
         out["_dh4p"] = dpred
         args = (self._p(self.params), self._p(batch["I1_aug"]), self._p(batch["I2_aug"]), self._p(dpred), self._p(self.grads),
                 self._p(self.ws), self.ws_bytes, self.B, self.Pz, 1, self.numeric)
@@ -205,6 +207,9 @@ class HomographyEngine(object):
         a.idx_stride = 0 if pi is None else (pi.stride(0) if pi.dim() > 1 else 1)
         a.h4p, a.H, a.pred_I2 = dp(sb["h4p"]), dp(sb["H"]), dp(sb["pred"])
         a.dh4p, a.dH, a.scratch, a.sums = dp(sb["dh4p"]), dp(sb["dH"]), dp(sb["scratch"]), dp(sb["sums"])
+        if self.loss_type == "ssim_loss" and "dpm" not in sb:
+            sb["dpm"] = torch.zeros(self.B, self.Pz, self.Pz, device=self.device)
+        a.dpred_map = dp(sb.get("dpm"))
         a.photo_losses, a.h4p_metrics, a.per_sample = dp(sb["photo"]), dp(sb["metrics"]), dp(sb["per"])
         return a
 
@@ -218,8 +223,6 @@ class HomographyEngine(object):
     def train_step(self, batch):
         """One optimiser step.  The whole forward/backward is ONE C call (udh_step_forward_backward); result tensors are
         the engine's static buffers (valid until the next step)."""
-        if self.loss_type not in _lib.STEP_LOSS:
-            raise _lib.UdhError("loss_type %s has no CUDA backward yet (SURVEY §8f item 3)" % self.loss_type)
         a = self._fill_args(batch, True)
         st = ops._stream()
         if self.world_size == 1:

@@ -84,15 +84,23 @@ def warp_loss_forward(I, H, I2, patch_indices, pw, ph, want_pred=True, sums=None
     return pred, sums
 
 
-def warp_loss_backward(I, H, I2, patch_indices, pw, ph, loss_type, sums, upstream=1.0):
+def ssim_backward(pred, I2, pw, ph):
+    """d ssim_loss / d pred [B,ph,pw] (homography_model.py:141-158,316)."""
+    B = pred.shape[0]
+    dpred = torch.empty(B, ph, pw, device=pred.device, dtype=torch.float32)
+    check(lib.udh_ssim_bwd(_ptr(pred), _ptr(I2), pw, ph, _ptr(dpred), B, _stream()), "udh_ssim_bwd")
+    return dpred
+
+
+def warp_loss_backward(I, H, I2, patch_indices, pw, ph, loss_type, sums, upstream=1.0, dpred=None):
     B, Hh, W, C = _img_args(I)
     stride = 0
     if patch_indices is not None:
         stride = patch_indices.stride(0) if patch_indices.dim() > 1 else 1
     dH = torch.empty(B, 3, 3, device=I.device, dtype=torch.float32)
     scratch = torch.empty(B * 9, device=I.device, dtype=torch.float32)
-    check(lib.udh_warp_loss_bwd(_ptr(I), C, Hh, W, _ptr(H), _ptr(I2), _ptr(patch_indices), stride, pw, ph, loss_type,
-                                _ptr(sums), float(upstream), _ptr(dH), _ptr(scratch), B, _stream()), "udh_warp_loss_bwd")
+    check(lib.udh_warp_loss_bwd_ex(_ptr(I), C, Hh, W, _ptr(H), _ptr(I2), _ptr(patch_indices), stride, pw, ph, loss_type,
+                                   _ptr(sums), _ptr(dpred), float(upstream), _ptr(dH), _ptr(scratch), B, _stream()), "udh_warp_loss_bwd_ex")
     return dH
 
 
