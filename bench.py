@@ -334,6 +334,24 @@ def other_configs(torch, _lib, engine, synthetic, numeric, peaks, dev):
     import ctypes
     out = {}
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    if numeric != "fp32":
+        try:
+            # the same headline workload in the fp32 parity mode (the mode the 1e-3 px parity tests certify)
+            eng = engine.HomographyEngine(PER_GPU_BATCH, numeric="fp32", seed=0, loss_type="h_loss", lr=5e-4, device=dev)
+            bs = [synthetic.make_batch(PER_GPU_BATCH, seed=900 + i, device=dev) for i in range(2)]
+            for i in range(3):
+                eng.train_step(bs[i % 2])
+            e0, e1 = ev(), ev(); torch.cuda.synchronize(); e0.record()
+            n = 5
+            for i in range(n):
+                eng.train_step(bs[i % 2])
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out["configs[1] in fp32 parity mode (UDH_NUMERIC_FP32)"] = {"pairs_per_s": PER_GPU_BATCH / (ms * 1e-3), "ms_per_step": ms}
+            del eng, bs
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out["fp32 parity mode error"] = repr(e)[:200]
     try:
         B3 = 512
         eng = engine.HomographyEngine(B3, numeric=numeric, seed=0, device=dev)

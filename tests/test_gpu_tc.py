@@ -144,3 +144,34 @@ def test_bf16_mean_corner_error_vs_oracle_golden(udh, golden_dir):
         assert abs(d["h_loss"] - float(g["s%d_h_loss" % seed])) <= 1e-3
         assert np.abs(out["pred_h4p"].cpu().numpy() - g["s%d_pred_h4p" % seed]).max() <= 2e-3
         assert d["num_fail"] == float(g["s%d_num_fail" % seed])
+
+
+def test_bf16_full_size_properties_B128(udh):
+    """BASELINE configs[1] size (B = 128) in the tensor-core mode: replicated samples agree with the B = 4 run (the tiling
+    of the padded streams must not leak between images), the mean corner error agrees with the fp32 mode to 1e-3 px, and a
+    train step leaves finite, non-trivial updates in every parameter tensor."""
+    B = 128
+    batch = O.make_batch(100, 4)
+    rep = lambda t: t.repeat(B // 4, *([1] * (t.dim() - 1))).cuda().contiguous()
+    db = {k: rep(v) for k, v in batch.items() if isinstance(v, torch.Tensor) and k != "H_gt"}
+    e16 = udh.engine.HomographyEngine(B, seed=0, numeric="bf16", loss_type="h_loss", lr=5e-4)
+    out = e16.forward(db, train=False)
+    h = out["pred_h4p"].clone()
+    assert (h[:4] - h[4:8]).abs().max().item() < 1e-5 and (h[:4] - h[-4:]).abs().max().item() < 1e-5
+    e4 = udh.engine.HomographyEngine(4, seed=0, numeric="bf16")
+    h4 = e4.forward(dev(batch), train=False)["pred_h4p"]
+    assert (h4 - h[:4]).abs().max().item() < 1e-5
+    e32 = udh.engine.HomographyEngine(B, seed=0, numeric="fp32")
+    d32, d16 = e32.losses_dict(e32.forward(db, train=False)), e16.losses_dict(out)
+    assert abs(d32["bounded_h_loss"] - d16["bounded_h_loss"]) <= 1e-3 and abs(d32["h_loss"] - d16["h_loss"]) <= 1e-3
+    assert d32["num_fail"] == d16["num_fail"]
+    del e32
+    p0 = e16.params.clone()
+    e16.train_step(db)
+    specs = udh.params.param_specs()
+    upd = (e16.params - p0)
+    assert torch.isfinite(e16.params).all()
+    for name, s in specs.items():
+        u = upd[s.offset:s.offset + s.size]
+        assert u.abs().max().item() > 0, name                     # every tensor received a gradient
+        assert u.abs().max().item() <= 5e-4 * 1.01, name          # first TF-Adam step is bounded by lr
