@@ -403,14 +403,19 @@ int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, cons
   uint64_t dB[2] = {b_inner, b_outer}, sB[2] = {2, b_inner * 2};
   uint32_t boxB[2] = {64, B_MN ? 64u : 256u};
   TRY(tc::make_tmap_bf16(&tmB, Bm, 2, dB, sB, boxB));
-  const size_t smem = 1024 + (size_t)tc::kGemmStages * tc::kGemmStageBytes + 256;
+  // output map for the TMA-store epilogue: fp32 [M][ldc], box = 32 floats (128 B) x 32 rows
+  CUtensorMap tmC;
+  uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[2] = {4, (uint64_t)ldc * 4};
+  uint32_t boxC[2] = {32, 32};
+  TRY(tc::make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, 2, dC, sC, boxC));
+  const size_t smem = 1024 + (size_t)tc::kGemmStages * tc::kGemmStageBytes + (ATOMIC ? 0 : tc::kGemmEpiBytes) + 256;
   auto kern = tc::tc_gemm_kernel<A_MN, B_MN, ATOMIC>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
-  kern<<<tiles < sms ? tiles : sms, 256, smem, st>>>(tmA, tmB, g, C);
+  kern<<<tiles < sms ? tiles : sms, 256, smem, st>>>(tmA, tmB, tmC, g, C);
   return check_launch("tc_gemm_kernel");
 }
 

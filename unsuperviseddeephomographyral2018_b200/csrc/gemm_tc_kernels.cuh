@@ -22,13 +22,18 @@ struct GemmGeom {
 constexpr int kGemmStages = 4;
 constexpr int kGemmStageBytes = 16384 + 32768;   // A 128 x 64, B 256 x 64 (bf16)
 
+constexpr int kGemmEpiBytes = 4 * 32 * 128;      // TMA-store staging of the non-atomic epilogue: 32 rows x 32 floats per warp
+
+// ATOMIC: split-K partial tiles are added with 16-byte vector reductions.  Otherwise the tile is stored through a swizzled
+// shared-memory staging block and TMA (full 128-byte lines; rows / columns beyond M / N are clipped by the tensor map).
 template <bool A_MN, bool B_MN, bool ATOMIC>
 __global__ void __launch_bounds__(256, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmGeom g,
-               float* __restrict__ C) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+               const GemmGeom g, float* __restrict__ C) {
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)kGemmStages * kGemmStageBytes);
+  uint8_t* sEpi = base + (size_t)kGemmStages * kGemmStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + (ATOMIC ? 0 : kGemmEpiBytes));
   uint64_t* full = bars;                       // [stages]
   uint64_t* empty = bars + kGemmStages;        // [stages]
   uint64_t* t_full = bars + 2 * kGemmStages;   // [2]
@@ -110,6 +115,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
+    uint8_t* stg = sEpi + ew * 4096;
+    const uint32_t my_row = smem_u32(stg) + lane * 128;
+    const int sw = lane & 7;
+    bool store_pending = false;
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
       int mt, nt, ks;
@@ -122,29 +131,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int c = 0; c < 8; ++c) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * 256 + c * 32), v);
-        if (m < g.M) {
-          const int n0 = nt * 256 + c * 32;
-          if (ATOMIC && n0 + 32 <= g.N) {
+        const int n0 = nt * 256 + c * 32;
+        if (ATOMIC) {
+          if (m < g.M) {
+            if (n0 + 32 <= g.N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) red_add_v4(crow + c * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else if (ATOMIC) {
+              for (int j = 0; j < 8; ++j) red_add_v4(crow + c * 32 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) atomicAdd(crow + c * 32 + j, v[j]);
-          } else if (n0 + 32 <= g.N) {
-            float4* p = reinterpret_cast<float4*>(crow + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < g.N) crow[c * 32 + j] = v[j];
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) atomicAdd(crow + c * 32 + j, v[j]);
+            }
           }
+        } else {
+          if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)((j4 ^ sw) << 4)), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]),
+                         "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3]) : "memory");
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && n0 < g.N && mt * 128 + ew * 32 < g.M) { tma_store_2d(&tmC, stg, n0, mt * 128 + ew * 32); bulk_commit(); }
+          store_pending = true;
         }
       }
       tc_fence_before();
       mbar_arrive(&t_empty[b]);
     }
+    if (!ATOMIC) { if (lane == 0) bulk_wait0(); __syncwarp(); }
   }
   tc_fence_before();
   __syncthreads();

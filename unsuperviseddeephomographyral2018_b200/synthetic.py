@@ -17,13 +17,21 @@ STD_I = (69.85, 68.81, 72.45)
 
 
 def _texture(gen, B, Hh, W, device):
-    n = torch.rand(B, 3, Hh, W, device=device, generator=gen)
-    k = torch.tensor([1., 4., 7., 4., 1.], device=device)
-    k = (k[:, None] * k[None, :]); k = (k / k.sum()).expand(3, 1, 5, 5).contiguous()
-    for _ in range(2):
-        n = F.conv2d(F.pad(n, (2, 2, 2, 2), mode="reflect"), k, groups=3)
-    lo = n.amin(dim=(1, 2, 3), keepdim=True); hi = n.amax(dim=(1, 2, 3), keepdim=True)
-    return ((n - lo) / (hi - lo) * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()   # NHWC uint8
+    """Seeded multi-octave random texture, uint8 NHWC: random grids at 1/1 ... 1/32 resolution, bicubically upsampled and
+    summed with amplitude proportional to their scale (roughly the 1/f spectrum of natural images), so photometric losses
+    see structure at the scale of the rho = 45 px displacements as well as fine detail."""
+    img = torch.zeros(B, 3, Hh, W, device=device)
+    for o in range(6):
+        s = 2 ** o
+        h, w = max(2, -(-Hh // s) + 1), max(2, -(-W // s) + 1)
+        g = torch.rand(B, 3, h, w, device=device, generator=gen) - 0.5
+        if o == 0:
+            g = F.avg_pool2d(F.pad(g, (1, 1, 1, 1), mode="reflect"), 3, 1)[..., :Hh, :W]
+        else:
+            g = F.interpolate(g, size=(h * s, w * s), mode="bicubic", align_corners=False)[..., :Hh, :W]
+        img = img + g * float(s) ** 0.9
+    lo = img.amin(dim=(1, 2, 3), keepdim=True); hi = img.amax(dim=(1, 2, 3), keepdim=True)
+    return ((img - lo) / (hi - lo) * 255.0).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()   # NHWC uint8
 
 
 def normalise(img_u8):
