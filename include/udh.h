@@ -202,6 +202,10 @@ int udh_prep_inputs_u8(const uint8_t* I, const uint8_t* I_prime, const float* pt
  * udh_prof_read synchronises on them and returns the accumulated device time and the number of brackets.
  * Must be off while a stream is being captured into a CUDA graph. */
 unsigned long long udh_launch_count(void);
+/* Leave n SMs free in the persistent one-CTA-per-SM tensor-core kernels (process-wide).  Used in data-parallel runs so
+ * that the NCCL allreduce kernel overlapping the backward gets its own SMs instead of displacing persistent CTAs (a
+ * displaced CTA would only start after another one finishes, i.e. serialise its whole share of the work). */
+int udh_set_sm_reserve(int n);
 int udh_prof_enable(int on);
 int udh_prof_reset(void);
 int udh_prof_num_tags(void);

@@ -20,6 +20,15 @@ enum ProfTag {
   PROF_H4P_LOSS, PROF_ADAM, PROF_ELTWISE, PROF_TC_PREP, PROF_NUM_TAGS
 };
 extern unsigned long long g_launches;
+extern int g_sm_reserve;      // SMs the persistent tensor-core kernels leave free (udh_set_sm_reserve)
+// CTAs a persistent one-CTA-per-SM kernel should launch on the current device
+inline int persistent_ctas() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int n = sms - g_sm_reserve;
+  return n > 0 ? n : 1;
+}
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 struct ProfScope {

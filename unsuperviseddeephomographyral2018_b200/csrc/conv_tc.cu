@@ -213,9 +213,7 @@ int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const 
                      uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, size_t smem, cudaStream_t st) {
   auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
   kern<<<grid, 256, smem, st>>>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
   return check_launch("tc_conv_kernel");
@@ -347,9 +345,7 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   UDH_REQUIRE(smem <= 232448, "tc wgrad: %zu bytes of shared memory exceed the 227 KiB limit", smem);
   auto kern = tc::tc_wgrad_kernel<N_OUT, CBX, T>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_ctas();
   int gx = sms / gy;
   if (gx > g.num_items) gx = g.num_items;
   if (gx < 1) gx = 1;
@@ -411,9 +407,7 @@ int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, cons
   const size_t smem = 1024 + (size_t)tc::kGemmStages * tc::kGemmStageBytes + (ATOMIC ? 0 : tc::kGemmEpiBytes) + 256;
   auto kern = tc::tc_gemm_kernel<A_MN, B_MN, ATOMIC>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = persistent_ctas();
   const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
   kern<<<tiles < sms ? tiles : sms, 256, smem, st>>>(tmA, tmB, tmC, g, C);
   return check_launch("tc_gemm_kernel");
@@ -431,7 +425,7 @@ int conv1_tc_fwd(const float* I1, const float* I2, const float* w, const float* 
   TRY(tc::make_tmap_bf16(&tmOut, out_pad, 2, dims, str, box));
   const size_t smem = 1024 + 2 * 16384 + 8192 + 16384 + 256;
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = g.tiles < 296 ? g.tiles : 296;
+  const int grid = g.tiles < 2 * persistent_ctas() ? g.tiles : 2 * persistent_ctas();
   tc::conv1_tc_fwd_kernel<<<grid, 160, smem, st>>>(tmOut, g, I1, I2, w, bias, mask_out);
   return check_launch("conv1_tc_fwd_kernel");
 }
@@ -447,7 +441,7 @@ int conv1_tc_wgrad(const float* I1, const float* I2, const __nv_bfloat16* G_pad,
   TRY(tc::make_tmap_bf16(&tmG, G_pad, 2, dims, str, box));
   const size_t smem = 1024 + 4 * 16384 + 256;
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = g.tiles < 296 ? g.tiles : 296;
+  const int grid = g.tiles < 2 * persistent_ctas() ? g.tiles : 2 * persistent_ctas();
   tc::conv1_tc_wgrad_kernel<<<grid, 160, smem, st>>>(tmG, g, I1, I2, dW, db);
   return check_launch("conv1_tc_wgrad_kernel");
 }

@@ -15,6 +15,7 @@ void set_error(const char* fmt, ...) {
 }
 
 unsigned long long g_launches = 0;
+int g_sm_reserve = 0;
 
 namespace {
 const char* kTagNames[PROF_NUM_TAGS] = {
@@ -120,6 +121,12 @@ extern "C" int udh_device_available(void) {
 }
 
 extern "C" unsigned long long udh_launch_count(void) { return udh::g_launches; }
+
+extern "C" int udh_set_sm_reserve(int n) {
+  UDH_REQUIRE(n >= 0 && n < 128, "udh_set_sm_reserve: bad value %d", n);
+  udh::g_sm_reserve = n;
+  return UDH_OK;
+}
 
 extern "C" int udh_prof_enable(int on) {
   if (on && !udh::g_tags) udh::g_tags = new udh::TagState[udh::PROF_NUM_TAGS];

@@ -62,6 +62,9 @@ class HomographyEngine(object):
         self.pg = process_group
         self.world_size = world_size
         self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
+        if world_size > 1:
+            import os
+            check(lib.udh_set_sm_reserve(int(os.environ.get("UDH_SM_RESERVE", "0"))), "udh_set_sm_reserve")
         # static per-step outputs of the one-call step (udh_step_forward_backward): reused every step
         B, Pz, dev = self.B, self.Pz, self.device
         self._sb = dict(h4p=torch.zeros(B, 8, device=dev), H=torch.zeros(B, 3, 3, device=dev), pred=torch.zeros(B, Pz, Pz, 1, device=dev),
