@@ -73,7 +73,6 @@ class HomographyEngine(object):
                         metrics=torch.zeros(_lib.NMETRICS, device=dev), per=torch.zeros(B, device=dev))
         self._args = _lib.StepArgs()
         self.dropout_seed = 0x5EED0000 + (seed or 0)
-        self.kernel_launches = 0   # kernels launched by the last forward/backward/update (counted, see _count)
 
     # ------------------------------------------------------------------ parameters
     def load_flat(self, flat_np):
