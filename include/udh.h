@@ -130,6 +130,11 @@ size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode);
 int udh_cnn_workspace_init(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void* stream);
 int udh_cnn_fwd(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes, int B,
                 int P, int train, uint64_t seed, int numeric_mode, void* stream);
+/* flags: UDH_FWD_FC1_MIRROR_CURRENT — the workspace's bf16 copy of fc1's weights already matches `params`
+ * (udh_adam_step_mirror wrote it, or a previous forward did and params are unchanged): skip the conversion. */
+#define UDH_FWD_FC1_MIRROR_CURRENT 1
+int udh_cnn_fwd_ex(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes, int B,
+                   int P, int train, uint64_t seed, int numeric_mode, int flags, void* stream);
 /* dh4p[B,8] -> grads (ACCUMULATED into the flat buffer: caller zeroes it once per step). */
 int udh_cnn_bwd(const float* params, const float* I1, const float* I2, const float* dh4p, float* grads, void* ws,
                 size_t ws_bytes, int B, int P, int train, int numeric_mode, void* stream);
@@ -158,6 +163,18 @@ size_t udh_param_total_floats(int P);
  * computed by the caller (t is 1-based).  If zero_grad != 0 the gradient buffer is cleared in the same pass. */
 int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                   float eps, float grad_scale, int zero_grad, void* stream);
+/* Same update, fused with the refresh of a bf16 weight mirror (UDH_NUMERIC_BF16): the updated parameters of the float
+ * range [mirror_begin, mirror_begin + mirror_count) are also written, rounded to bf16, to `mirror`; with
+ * mirror_keep_grad != 0 the gradient of that range is not cleared (its producer stores rather than accumulates).
+ * udh_cnn_fc1_mirror names the range and the buffer for fc1's weights; a forward pass that follows may then be given
+ * UDH_FWD_FC1_MIRROR_CURRENT and skips its own fp32 -> bf16 conversion of the 128 MB tensor. */
+int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                         float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin, size_t mirror_count,
+                         int mirror_keep_grad, void* stream);
+/* bf16 copy of fc1's weights inside the workspace: *mirror (NULL in UDH_NUMERIC_FP32), its float range in the flat
+ * parameter buffer, and whether fc1's weight gradient is stored (1) or accumulated (0) by the backward pass. */
+int udh_cnn_fc1_mirror(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void** mirror, size_t* param_begin,
+                       size_t* count, int* grad_is_stored);
 
 /* ---- one call per step -------------------------------------------------------------------------------------------
  * The reference runs a step as ONE sess.run([apply_grad_opt, losses...]) (homography_CNN_synthetic.py:335-345).
@@ -186,6 +203,7 @@ typedef struct {
   float* dpred_map;               /* [B,P,P] scratch, only for UDH_STEP_LOSS_SSIM */
   double* sums;                   /* [UDH_NSUMS] */
   float *photo_losses, *h4p_metrics, *per_sample;   /* [UDH_NLOSSES], [UDH_NMETRICS], [B] or NULL */
+  int fwd_flags;                  /* UDH_FWD_* */
 } udh_step_args;
 int udh_step_forward_backward(const udh_step_args* args, int phase, void* stream);
 

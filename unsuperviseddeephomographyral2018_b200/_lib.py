@@ -26,7 +26,10 @@ class StepArgs(ctypes.Structure):
                 ("patch_indices", c_void_p), ("idx_stride", c_int64),
                 ("h4p", c_void_p), ("H", c_void_p), ("pred_I2", c_void_p),
                 ("dh4p", c_void_p), ("dH", c_void_p), ("scratch", c_void_p), ("dpred_map", c_void_p), ("sums", c_void_p),
-                ("photo_losses", c_void_p), ("h4p_metrics", c_void_p), ("per_sample", c_void_p)]
+                ("photo_losses", c_void_p), ("h4p_metrics", c_void_p), ("per_sample", c_void_p), ("fwd_flags", c_int)]
+
+
+FWD_FC1_MIRROR_CURRENT = 1
 
 
 STEP_ALL, STEP_FWD_HEAD, STEP_CONVS, STEP_FWD_ONLY = 0, 1, 2, 3
@@ -55,6 +58,10 @@ SIGNATURES = {
     "udh_cnn_workspace_init": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "udh_cnn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_uint64, c_int,
                             c_void_p]),
+    "udh_cnn_fwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_uint64, c_int,
+                               c_int, c_void_p]),
+    "udh_cnn_fc1_mirror": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t),
+                                   POINTER(c_int)]),
     "udh_cnn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                             c_void_p]),
     "udh_cnn_bwd_phase": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
@@ -65,6 +72,8 @@ SIGNATURES = {
     "udh_param_total_floats": (c_size_t, [c_int]),
     "udh_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
                               c_int, c_void_p]),
+    "udh_adam_step_mirror": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
+                                     c_int, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),
     "udh_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "udh_debug_tc_conv_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "udh_debug_tc_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

@@ -134,8 +134,26 @@ extern "C" int udh_cnn_activation(void* ws, size_t ws_bytes, int B, int P, int n
   return UDH_OK;
 }
 
+extern "C" int udh_cnn_fc1_mirror(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void** mirror, size_t* param_begin,
+                                  size_t* count, int* grad_is_stored) {
+  TRY(check_cnn_args("udh_cnn_fc1_mirror", B, P, numeric_mode));
+  Workspace L(B, P, numeric_mode);
+  UDH_REQUIRE(ws && ws_bytes >= L.total && mirror && param_begin && count && grad_is_stored, "udh_cnn_fc1_mirror: bad arguments");
+  ParamLayout PL(P);
+  *param_begin = PL.off[16];
+  *count = (size_t)(P / 8) * (P / 8) * 128 * 1024;
+  *mirror = numeric_mode == UDH_NUMERIC_BF16 ? tc_fc1_mirror(ws, L.tc, B, P) : nullptr;
+  *grad_is_stored = numeric_mode == UDH_NUMERIC_BF16 ? 1 : 0;
+  return UDH_OK;
+}
+
 extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes,
                            int B, int P, int train, uint64_t seed, int numeric_mode, void* stream) {
+  return udh_cnn_fwd_ex(params, I1, I2, h4p, ws, ws_bytes, B, P, train, seed, numeric_mode, 0, stream);
+}
+
+extern "C" int udh_cnn_fwd_ex(const float* params, const float* I1, const float* I2, float* h4p, void* ws, size_t ws_bytes,
+                              int B, int P, int train, uint64_t seed, int numeric_mode, int flags, void* stream) {
   TRY(check_cnn_args("udh_cnn_fwd", B, P, numeric_mode));
   UDH_REQUIRE(params && I1 && I2 && h4p && ws, "udh_cnn_fwd: null pointer");
   Workspace L(B, P, numeric_mode);
@@ -178,7 +196,7 @@ extern "C" int udh_cnn_fwd(const float* params, const float* I1, const float* I2
   ProfScope ps_fc(PROF_FC_FWD, st);
   UDH_CUDA(cudaMemsetAsync(at<float>(ws, L.fc1_acc), 0, (size_t)B * 1024 * 4, st));
   if (numeric_mode == UDH_NUMERIC_BF16) {
-    TRY(tc_fc1_fwd(feat_in, params + PL.off[16], at<float>(ws, L.fc1_acc), ws, L.tc, B, P, st));
+    TRY(tc_fc1_fwd(feat_in, params + PL.off[16], at<float>(ws, L.fc1_acc), ws, L.tc, B, P, (flags & UDH_FWD_FC1_MIRROR_CURRENT) != 0, st));
   } else {
     TRY(sgemm_simt(feat_in, feat, 1, params + PL.off[16], 1024, 1, at<float>(ws, L.fc1_acc), 1024, B, 1024, feat,
                    B <= 256 ? 16 : 4, 0, st));

@@ -26,6 +26,7 @@ struct TcLayout {
   size_t numel[11];  // padded element counts
   size_t wf[8], wd[8];   // packed bf16 weights, forward / dgrad (rotated)
   size_t Mb[8];      // 1-bit ReLU masks [Q][C/32] uint32 of the conv outputs a dgrad needs (layers 0, 2, 4, 6)
+  size_t Px[3];      // max-pool routing codes [B][H/2][W/2][C/8] uint32 (3 bits per channel), written by the forward
   size_t fc_x, fc_w, fc_dy;   // bf16 copies for the fc1 GEMMs: x [B,F], W [F,1024], dy [B,1024]
   size_t total;
   TcLayout(int B, int P_) {
@@ -42,6 +43,7 @@ struct TcLayout {
     for (int i = 0; i < 11; ++i) G[i] = take(numel[i] * 2);
     for (int i = 0; i < 8; ++i) { wf[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); wd[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); }
     for (int i = 0; i < 8; ++i) Mb[i] = (i % 2 == 0) ? take(numel[i] / 8) : 0;
+    for (int i = 0; i < 3; ++i) Px[i] = take((size_t)B * (P_ >> (i + 1)) * (P_ >> (i + 1)) * (i == 2 ? 16 : 8) * 4);
     const size_t feat = (size_t)(P_ / 8) * (P_ / 8) * 128;
     fc_x = take((size_t)B * feat * 2);
     fc_w = take(feat * 1024 * 2);
@@ -150,7 +152,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // 2x2/2 max pool on padded bf16 streams: in [B,H+2,W+2,C] -> out [B,H/2+2,W/2+2,C]
-__global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C) {
+// Also records, per channel, which of the four inputs won (first maximum in scan order) or 4 when the maximum is not
+// positive (the producer's ReLU passes no gradient): 3 bits per channel, 8 channels per uint32 -> the backward pass routes
+// gradients from these codes and never re-reads the pre-pool activations.
+__global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ codes,
+                                     int B, int H, int W, int C) {
   const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
   const size_t total = (size_t)B * OH * OW * C8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -166,13 +172,23 @@ __global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_
     unpack8(__ldg(reinterpret_cast<const uint4*>(p + (size_t)(W + 2) * C)), c);
     unpack8(__ldg(reinterpret_cast<const uint4*>(p + (size_t)(W + 2) * C + C)), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+    uint32_t code = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = a[j]; uint32_t k = 0;
+      if (b[j] > v) { v = b[j]; k = 1; }
+      if (c[j] > v) { v = c[j]; k = 2; }
+      if (d[j] > v) { v = d[j]; k = 3; }
+      m[j] = v;
+      code |= (v > 0.f ? k : 4u) << (3 * j);
+    }
     *reinterpret_cast<uint4*>(out + (((size_t)n * (OH + 2) + oy + 1) * (OW + 2) + ox + 1) * C + c8 * 8) = pack8(m);
+    codes[i] = code;
   }
 }
 
-// gradient routing of the above + ReLU mask of the producer (first arg-max in scan order, only where it is > 0)
-__global__ void pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ gout,
+// gradient routing of the above + ReLU mask of the producer, from the forward's routing codes
+__global__ void pool_bwd_bf16_kernel(const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ gout,
                                      __nv_bfloat16* __restrict__ gin, int B, int H, int W, int C) {
   const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
   const size_t total = (size_t)B * OH * OW * C8;
@@ -184,20 +200,13 @@ __global__ void pool_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, const
     const int n = r / OH;
     const size_t base = (((size_t)n * (H + 2) + 2 * oy + 1) * (W + 2) + 2 * ox + 1) * C + c8 * 8;
     const size_t rowp = (size_t)(W + 2) * C;
-    float a[8], b[8], c[8], d[8], g[8], oa[8], ob[8], oc[8], od[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base)), a);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + C)), b);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + rowp)), c);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(in + base + rowp + C)), d);
+    const uint32_t code = __ldg(codes + i);
+    float g[8], oa[8], ob[8], oc[8], od[8];
     unpack8(__ldg(reinterpret_cast<const uint4*>(gout + (((size_t)n * (OH + 2) + oy + 1) * (OW + 2) + ox + 1) * C + c8 * 8)), g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float m = a[j]; int k = 0;
-      if (b[j] > m) { m = b[j]; k = 1; }
-      if (c[j] > m) { m = c[j]; k = 2; }
-      if (d[j] > m) { m = d[j]; k = 3; }
-      const float v = m > 0.f ? g[j] : 0.f;
-      oa[j] = k == 0 ? v : 0.f; ob[j] = k == 1 ? v : 0.f; oc[j] = k == 2 ? v : 0.f; od[j] = k == 3 ? v : 0.f;
+      const uint32_t k = (code >> (3 * j)) & 7u;
+      oa[j] = k == 0 ? g[j] : 0.f; ob[j] = k == 1 ? g[j] : 0.f; oc[j] = k == 2 ? g[j] : 0.f; od[j] = k == 3 ? g[j] : 0.f;
     }
     *reinterpret_cast<uint4*>(gin + base) = pack8(oa);
     *reinterpret_cast<uint4*>(gin + base + C) = pack8(ob);
@@ -280,42 +289,15 @@ int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, c
   unpad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
   return check_launch("unpad_cast");
 }
-int pool_fwd_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int H, int W, int C, cudaStream_t st) {
+int pool_fwd_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, uint32_t* codes, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  pool_fwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, out, B, H, W, C);
+  pool_fwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, out, codes, B, H, W, C);
   return check_launch("pool_fwd_bf16");
 }
-int pool_bwd_bf16(const __nv_bfloat16* in, const __nv_bfloat16* gout, __nv_bfloat16* gin, int B, int H, int W, int C, cudaStream_t st) {
+int pool_bwd_bf16(const uint32_t* codes, const __nv_bfloat16* gout, __nv_bfloat16* gin, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  pool_bwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, gout, gin, B, H, W, C);
+  pool_bwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(codes, gout, gin, B, H, W, C);
   return check_launch("pool_bwd_bf16");
-}
-
-// db[c] += sum over all positions of a padded bf16 stream [Q][C] (borders are zero).  C in {64,128}.
-// thread = 8 channels (one 16-byte load) of one position per iteration; block-level reduction, then atomics.
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ gsrc, float* __restrict__ db, int Q, int C) {
-  __shared__ float red[256][9];
-  const int lanes = C >> 3;                       // threads per position
-  const int ppb = 256 / lanes;                    // positions per block iteration
-  const int sub = threadIdx.x % lanes, prow = threadIdx.x / lanes;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int q = blockIdx.x * ppb + prow; q < Q; q += gridDim.x * ppb) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(gsrc + (size_t)q * C + sub * 8)), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += f[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
-  __syncthreads();
-  if (threadIdx.x < lanes) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
-      for (int r = 0; r < ppb; ++r) s += red[r * lanes + threadIdx.x][j];
-      atomicAdd(db + threadIdx.x * 8 + j, s);
-    }
-  }
 }
 
 template <int N_OUT, int CBX, int T>
@@ -327,10 +309,16 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   const int tiles = (g.Q + 127) / 128;
   g.num_items = (tiles + T - 1) / T;
   g.xrows = T * 128 + 2 * g.hh;
-  g.num_groups = CBX == 1 ? 5 : 9;
-  g.groups_per_y = 512 / N_OUT < g.num_groups ? (CBX == 1 ? 3 : 3) : g.num_groups;     // accumulators of one slice fit TMEM
-  if (g.groups_per_y * N_OUT > 512) g.groups_per_y = 512 / N_OUT;
-  const int gy = (g.num_groups + g.groups_per_y - 1) / g.groups_per_y;
+  g.num_groups = CBX == 1 ? 5 : 10;
+  const int sms = persistent_ctas();
+  const int max_groups = 512 / N_OUT;                              // accumulators of one slice fit TMEM
+  g.num_slices = (g.num_groups + max_groups - 1) / max_groups;
+  g.slice_group[0] = 0; g.slice_cta[0] = 0;
+  for (int s = 0; s < g.num_slices; ++s) {
+    g.slice_group[s + 1] = g.slice_group[s] + g.num_groups / g.num_slices + (s < g.num_groups % g.num_slices ? 1 : 0);
+    g.slice_cta[s + 1] = (int)((long long)sms * g.slice_group[s + 1] / g.num_groups);
+    if (g.slice_cta[s + 1] <= g.slice_cta[s]) g.slice_cta[s + 1] = g.slice_cta[s] + 1;
+  }
   constexpr int CBO = N_OUT / 64;
   const int Cin = CBX * 64;
   CUtensorMap tmX128, tmXhh, tmG;
@@ -341,21 +329,12 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   uint64_t dimsG[2] = {(uint64_t)N_OUT, (uint64_t)g.Q}, strG[2] = {2, (uint64_t)N_OUT * 2};
   TRY(tc::make_tmap_bf16(&tmG, gsrc, 2, dimsG, strG, box128));
   const size_t stage = (size_t)CBX * g.xrows * 128 + (size_t)CBO * T * 16384;
-  const size_t smem = 1024 + 2 * stage + (CBX == 1 ? 16384 : 0) + 256;
+  const size_t smem = 1024 + 2 * stage + 16384 + 256;
   UDH_REQUIRE(smem <= 232448, "tc wgrad: %zu bytes of shared memory exceed the 227 KiB limit", smem);
   auto kern = tc::tc_wgrad_kernel<N_OUT, CBX, T>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int sms = persistent_ctas();
-  int gx = sms / gy;
-  if (gx > g.num_items) gx = g.num_items;
-  if (gx < 1) gx = 1;
-  kern<<<dim3(gx, gy), 256, smem, st>>>(tmX128, tmXhh, tmG, g, dW, CBX == 1 ? db : nullptr);
-  TRY(check_launch("tc_wgrad_kernel"));
-  if (CBX == 2 && db) {
-    colsum_bf16_kernel<<<148 * 8, 256, 0, st>>>(gsrc, db, g.Q, N_OUT);
-    TRY(check_launch("colsum_bf16"));
-  }
-  return UDH_OK;
+  kern<<<g.slice_cta[g.num_slices], 256, smem, st>>>(tmX128, tmXhh, tmG, g, dW, db);
+  return check_launch("tc_wgrad_kernel");
 }
 
 // dW (HWIO fp32) += X^T-shifted . G ; db += sum G   for one layer, on padded bf16 streams
@@ -496,7 +475,7 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
     }
     if (i == 1 || i == 3 || i == 5) {
       ProfScope ps(PROF_POOL_FWD, st);
-      TRY(pool_fwd_bf16(Pb(i), Pb(8 + i / 2), B, s, s, kConv[i].cout, st));
+      TRY(pool_fwd_bf16(Pb(i), Pb(8 + i / 2), reinterpret_cast<uint32_t*>(tcw + L.Px[i / 2]), B, s, s, kConv[i].cout, st));
     }
   }
   return UDH_OK;
@@ -536,21 +515,26 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     }
     if (below_is_pool) {
       ProfScope ps(PROF_POOL_BWD, st);
-      TRY(pool_bwd_bf16(Pb(i - 1), Gb(below), Gb(i - 1), B, 2 * s, 2 * s, cin, st));
+      TRY(pool_bwd_bf16(reinterpret_cast<const uint32_t*>(tcw + L.Px[i / 2 - 1]), Gb(below), Gb(i - 1), B, 2 * s, 2 * s, cin, st));
     }
   }
   return UDH_OK;
 }
 
 // fc1 forward on tensor cores: acc[B,1024] (zeroed by the caller) += x[B,F] . W[F,1024]
-int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, cudaStream_t st) {
+void* tc_fc1_mirror(void* ws, size_t tc_off, int B, int P) {
+  TcLayout L(B, P);
+  return at<char>(ws, tc_off) + L.fc_w;
+}
+
+int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, bool w_mirror_current, cudaStream_t st) {
   TcLayout L(B, P);
   char* tcw = at<char>(ws, tc_off);
   const size_t feat = (size_t)(P / 8) * (P / 8) * 128;
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_x);
   __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_w);
   TRY(cast_bf16(x, xb, (size_t)B * feat, st));
-  TRY(cast_bf16(w, wb, feat * 1024, st));
+  if (!w_mirror_current) TRY(cast_bf16(w, wb, feat * 1024, st));
   const int kb = (int)(feat / 64);
   int splits = 32;
   while (kb % splits) splits >>= 1;

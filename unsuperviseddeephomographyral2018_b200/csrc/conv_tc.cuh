@@ -20,7 +20,8 @@ int tc_cnn_bwd_convs(const float* params, const size_t* param_off, const float* 
                      float* gB, void* ws, const size_t* act_off, size_t tc_off, int B, int P, cudaStream_t st);
 
 // fc1 (32768 -> 1024) on tensor cores; bf16 copies of x / W / dy live in the tensor-core workspace region.
-int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, cudaStream_t st);
+int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, bool w_mirror_current, cudaStream_t st);
+void* tc_fc1_mirror(void* ws, size_t tc_off, int B, int P);
 int tc_fc1_bwd(const float* dy, float* dW, float* dx, void* ws, size_t tc_off, int B, int P, cudaStream_t st);
 
 }  // namespace udh

@@ -1,4 +1,5 @@
 // Small entry points: error reporting, h4p losses / test metrics (Row L), TF-1 Adam (Row O).
+#include <cuda_bf16.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(256) h4p_loss_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, float alpha, float b1, float b2,
-                                                   float eps, float gs, int zero_grad) {
+                                                   float eps, float gs, int zero_grad, uint2* __restrict__ mirror,
+                                                   size_t mb4, size_t me4, int keep_grad) {
   const float c1 = 1.0f - b1, c2 = 1.0f - b2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
@@ -103,7 +105,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
     pv.x -= alpha * mv.x / (sqrtf(vv.x) + eps); pv.y -= alpha * mv.y / (sqrtf(vv.y) + eps);
     pv.z -= alpha * mv.z / (sqrtf(vv.z) + eps); pv.w -= alpha * mv.w / (sqrtf(vv.w) + eps);
     p[i] = pv; m[i] = mv; v[i] = vv;
-    if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool in_mirror = i >= mb4 && i < me4;
+    if (in_mirror) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      mirror[i - mb4] = pk;
+    }
+    if (zero_grad && !(in_mirror && keep_grad)) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -169,7 +177,16 @@ extern "C" int udh_h4p_loss(const float* pred, const float* gt, int B, float* me
 
 extern "C" int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                              float eps, float grad_scale, int zero_grad, void* stream) {
+  return udh_adam_step_mirror(p, g, m, v, n, alpha_t, beta1, beta2, eps, grad_scale, zero_grad, nullptr, 0, 0, 0, stream);
+}
+
+extern "C" int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                                    float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin,
+                                    size_t mirror_count, int mirror_keep_grad, void* stream) {
   UDH_REQUIRE(p && g && m && v, "udh_adam_step: null pointer");
+  if (!mirror) mirror_begin = mirror_count = 0;
+  UDH_REQUIRE(mirror_begin % 4 == 0 && mirror_count % 4 == 0 && mirror_begin + mirror_count <= n && (uintptr_t)mirror % 8 == 0,
+              "udh_adam_step_mirror: mirror range must be 4-float aligned and inside the buffer");
   UDH_REQUIRE(n % 4 == 0, "udh_adam_step: n must be a multiple of 4 (flat buffers are padded to 32 floats)");
   UDH_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "udh_adam_step: buffers must be 16-byte aligned");
   if (n == 0) return UDH_OK;
@@ -177,6 +194,7 @@ extern "C" int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, f
   const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   udh::ProfScope ps(udh::PROF_ADAM, udh::as_stream(stream));
   udh::adam_kernel<<<blocks, 256, 0, udh::as_stream(stream)>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
-                                                              beta1, beta2, eps, grad_scale, zero_grad);
+                                                              beta1, beta2, eps, grad_scale, zero_grad, (uint2*)mirror,
+                                                              mirror_begin / 4, (mirror_begin + mirror_count) / 4, mirror_keep_grad);
   return udh::check_launch("udh_adam_step");
 }

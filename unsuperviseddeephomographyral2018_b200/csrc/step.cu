@@ -16,7 +16,7 @@ extern "C" int udh_step_forward_backward(const udh_step_args* a, int phase, void
   if (phase != UDH_STEP_CONVS) {
     UDH_REQUIRE(a->params && a->I1 && a->I2 && a->I_aug && a->pts1 && a->h4p && a->H && a->sums && a->photo_losses && a->ws,
                 "udh_step_forward_backward: null pointer in args");
-    STEP_TRY(udh_cnn_fwd(a->params, a->I1, a->I2, a->h4p, a->ws, a->ws_bytes, B, P, a->train, a->seed, a->numeric_mode, stream));
+    STEP_TRY(udh_cnn_fwd_ex(a->params, a->I1, a->I2, a->h4p, a->ws, a->ws_bytes, B, P, a->train, a->seed, a->numeric_mode, a->fwd_flags, stream));
     const bool want_dpred = a->train && a->loss_type == UDH_STEP_LOSS_H && phase != UDH_STEP_FWD_ONLY;
     if (a->gt) STEP_TRY(udh_h4p_loss(a->h4p, a->gt, B, a->h4p_metrics, a->per_sample, want_dpred ? a->dh4p : nullptr, stream));
     STEP_TRY(udh_dlt_fwd(a->pts1, a->h4p, a->H, B, stream));

@@ -8,7 +8,8 @@
 //   Cin = 64  : TWO TAPS per MMA — the second 64-row M block is the same smem buffer shifted by (off_b - off_a) rows,
 //               expressed through the descriptor's leading-dimension byte offset; the odd tap 8 is paired with a block
 //               of ones, whose 64 identical result rows are the bias gradient sum_q G[q][co];
-//   Cin = 128 : one tap per MMA, the two 64-channel blocks of X are the two M blocks.
+//   Cin = 128 : one tap per MMA, the two 64-channel blocks of X are the two M blocks; a tenth group is an M = 64 MMA
+//               of the ones block against G, whose (identical) result rows are the bias gradient.
 // Accumulators stay in TMEM for the CTA's whole run (split-K over CTAs); one epilogue at the end adds them to the fp32
 // gradient buffer with atomics.  warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM alloc | warps 4-7: epilogue.
 #pragma once
@@ -21,8 +22,13 @@ struct WgradGeom {
   int Wp, Q, hh;
   int num_items;     // ceil(ceil(Q/128) / T)
   int xrows;         // T*128 + 2*hh rows staged per 64-channel block of X
-  int groups_per_y;  // MMA groups handled by one blockIdx.y slice
-  int num_groups;    // CBX == 1: 5 (4 tap pairs + tap 8 | ones);  CBX == 2: 9 taps
+  int num_groups;    // CBX == 1: 5 (4 tap pairs + tap 8 | ones);  CBX == 2: 10 (9 taps + ones)
+  // The accumulators of all groups do not fit the 512 TMEM columns when N_OUT = 128, so the groups are cut into slices;
+  // slice s owns groups [slice_group[s], slice_group[s+1]) and CTAs [slice_cta[s], slice_cta[s+1]) of the 1-D grid
+  // (CTA counts proportional to the slice's group count, so every CTA issues about the same number of MMAs).
+  int num_slices;
+  int slice_group[5];
+  int slice_cta[5];
 };
 
 template <int N_OUT, int CBX, int T>
@@ -37,19 +43,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
   const int gblk_bytes = T * 128 * 128;                         // one 64-channel block of G of one stage
   const int stage_bytes = CBX * xblk_bytes + CBO * gblk_bytes;
   uint8_t* sStage = base;                                       // [2][ X: CBX blocks | G: CBO blocks ]
-  uint8_t* sOnes = base + 2 * (size_t)stage_bytes;              // [128][128] bf16 ones (CBX == 1 only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (CBX == 1 ? 16384 : 0));
+  uint8_t* sOnes = base + 2 * (size_t)stage_bytes;              // [128][64] bf16 ones
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 16384);
   uint64_t* full = bars;        // [2]
   uint64_t* empty = bars + 2;   // [2]
   uint64_t* acc_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g_begin = blockIdx.y * g.groups_per_y;
-  const int g_count = min(g.groups_per_y, g.num_groups - g_begin);
+  int sl = 0;
+  while (sl + 1 < g.num_slices && (int)blockIdx.x >= g.slice_cta[sl + 1]) ++sl;
+  const int bx = (int)blockIdx.x - g.slice_cta[sl], gxs = g.slice_cta[sl + 1] - g.slice_cta[sl];
+  const int g_begin = g.slice_group[sl];
+  const int g_count = g.slice_group[sl + 1] - g_begin;
   constexpr int kTmemCols = 512;
 
-  if (CBX == 1) {
+  {
     // ones block: every 16-byte chunk is identical, so the 128-byte swizzle leaves it unchanged
     uint32_t* o = reinterpret_cast<uint32_t*>(sOnes);
     for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) o[i] = 0x3F803F80u;
@@ -66,13 +75,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int my_items = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_items = (g.num_items - bx + gxs - 1) / gxs;
 
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
         const int s = it & 1;
-        const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * T * 128;
+        const int q0 = (bx + it * gxs) * T * 128;
         mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
         uint8_t* st = sStage + (size_t)s * stage_bytes;
@@ -90,6 +99,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
   } else if (warp == 1) {
     // whole warp converged; one elected lane issues (see conv_tc_kernels.cuh)
     constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 1, 1);
+    constexpr uint32_t idesc_ones = make_idesc_bf16(64, N_OUT, 1, 1);
     const uint32_t ones_addr = smem_u32(sOnes);
     for (int it = 0; it < my_items; ++it) {
       const int s = it & 1;
@@ -114,18 +124,21 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
             } else {
               lbo = ones_addr - a_start;                      // second M block = the ones rows (bias gradient)
             }
-          } else {
+          } else if (gi < 9) {
             const int off = (gi / 3 - 1) * g.Wp + (gi % 3 - 1);
             a_start = x_addr + (uint32_t)(g.hh + t * 128 + off) * 128;
             lbo = (uint32_t)xblk_bytes;                       // second M block = channels 64..127
+          } else {
+            a_start = ones_addr; lbo = 0;                     // M = 64 rows of ones (bias gradient)
           }
+          const uint32_t id = (CBX == 2 && gi == 9) ? idesc_ones : idesc;
           const uint32_t a_lo = desc_lo(a_start, lbo);
           const uint32_t b_lo = desc_lo(g_addr + (uint32_t)t * 16384, (uint32_t)gblk_bytes);
           const uint32_t d_tmem = tmem_base + (uint32_t)(gl * N_OUT);
           if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)                     // 16 positions = 2048 bytes = 128 sixteen-byte units per k-step
-              umma_bf16(d_tmem, desc_from_lo(a_lo + kk * 128), desc_from_lo(b_lo + kk * 128), idesc, (it > 0 || t > 0 || kk > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, desc_from_lo(a_lo + kk * 128), desc_from_lo(b_lo + kk * 128), id, (it > 0 || t > 0 || kk > 0) ? 1u : 0u);
           }
           __syncwarp();
         }
@@ -151,9 +164,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
         if (tap == 9) is_ones = true;
       } else {
         ci = m; tap = gi;
+        if (gi == 9) is_ones = true;
       }
       float* dst = is_ones ? db : dW + ((size_t)tap * CIN + ci) * N_OUT;
-      const bool active = is_ones ? (m == 64 && db != nullptr) : true;
+      const bool active = is_ones ? (m == (CBX == 1 ? 64 : 0) && db != nullptr) : true;
 #pragma unroll 1
       for (int c = 0; c < N_OUT / 32; ++c) {
         float v[32];

@@ -58,6 +58,12 @@ class HomographyEngine(object):
         self.ws = torch.empty(self.ws_bytes, device=self.device, dtype=torch.uint8)
         check(lib.udh_cnn_workspace_init(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, ops._stream()),
               "udh_cnn_workspace_init")
+        # bf16 mode: Adam refreshes the bf16 copy of fc1's weights in the same pass, the next forward skips its conversion
+        mp, mb, mc, st = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_int()
+        check(lib.udh_cnn_fc1_mirror(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, ctypes.byref(mp), ctypes.byref(mb),
+                                     ctypes.byref(mc), ctypes.byref(st)), "udh_cnn_fc1_mirror")
+        self._mirror = (mp.value, mb.value, mc.value, st.value) if mp.value else None
+        self._mirror_current = False
         self.global_step = 0
         self.pg = process_group
         self.world_size = world_size
@@ -77,6 +83,7 @@ class HomographyEngine(object):
     # ------------------------------------------------------------------ parameters
     def load_flat(self, flat_np):
         self.params.copy_(torch.as_tensor(flat_np, dtype=torch.float32))
+        self._mirror_current = False          # any write to self.params outside update() must clear this
 
     def named_parameters(self):
         return P.unflatten(self.params, self.specs)
@@ -99,6 +106,7 @@ class HomographyEngine(object):
     def load_state_dict(self, sd, reset_step=False):
         self.params.copy_(sd["params"]); self.adam_m.copy_(sd["adam_m"]); self.adam_v.copy_(sd["adam_v"])
         self.global_step = 0 if reset_step else int(sd["global_step"])
+        self._mirror_current = False
 
     # ------------------------------------------------------------------ forward
     def _p(self, t):
@@ -189,8 +197,15 @@ class HomographyEngine(object):
         t = self.global_step + 1
         lr_t = learning_rate(self.global_step, self.lr, self.min_lr)
         alpha = lr_t * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
-        ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, alpha, 0.9, 0.999, 1e-8,
-                      1.0 / self.world_size, zero_grad=True)
+        if self._mirror is not None:
+            mp, mb, mc, stored = self._mirror
+            check(lib.udh_adam_step_mirror(self._p(self.params), self._p(self.grads), self._p(self.adam_m), self._p(self.adam_v),
+                                           self.params.numel(), alpha, 0.9, 0.999, 1e-8, 1.0 / self.world_size, 1,
+                                           ctypes.c_void_p(mp), mb, mc, stored, ops._stream()), "udh_adam_step_mirror")
+            self._mirror_current = True
+        else:
+            ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, alpha, 0.9, 0.999, 1e-8,
+                          1.0 / self.world_size, zero_grad=True)
         self.global_step += 1
         return lr_t
 
@@ -199,6 +214,7 @@ class HomographyEngine(object):
         I_aug = batch["I_aug"]
         a.B, a.P, a.img_h, a.img_w, a.C = self.B, self.Pz, I_aug.shape[1], I_aug.shape[2], I_aug.shape[3]
         a.numeric_mode, a.train = self.numeric, int(train)
+        a.fwd_flags = _lib.FWD_FC1_MIRROR_CURRENT if self._mirror_current else 0
         a.loss_type = _lib.STEP_LOSS.get(self.loss_type, -1)
         a.seed = self.dropout_seed + self.global_step
         dp = lambda t: t.data_ptr() if t is not None else None
