@@ -242,6 +242,10 @@ int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* 
  * scratch sized by udh_debug_tc_conv_scratch_bytes. */
 int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, float* db, void* scratch, int B, int H, int W, int cin,
                        int cout, void* stream);
+/* fused conv (64 -> 64 channels, W == 128) + bias + ReLU + 2x2 max-pool (conv1_2 + pool1): x [B,H,128,64] ->
+ * pooled [B,H/2,64,64] fp32 and routing codes [B,H/2,64,8] uint32 (3 bits per channel, 4 = no gradient). */
+int udh_debug_tc_conv_pool(const float* x, const float* w, const float* bias, float* pooled, uint32_t* codes, void* scratch,
+                           int B, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -208,3 +208,35 @@ def test_adam_refreshes_fc1_mirror(udh):
     assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
     fp = udh.engine.HomographyEngine(B, seed=0, numeric="fp32")
     assert fp._mirror is None
+
+
+@pytest.mark.parametrize("B,H", [(1, 4), (3, 128)])
+def test_tc_conv_pool_fused(udh, B, H):
+    """conv1_2 + pool1 in one kernel (row-pair tiles, 2x2 maximum in the epilogue) against torch on the same bf16-rounded
+    operands: pooled activations, and routing codes that must point at an element equal to the window maximum (4 exactly
+    where the maximum is not positive)."""
+    W = 128
+    g = torch.Generator(device="cuda").manual_seed(B * 31 + H)
+    x = torch.randn(B, H, W, 64, device="cuda", generator=g).bfloat16().float().contiguous()
+    w = (torch.randn(3, 3, 64, 64, device="cuda", generator=g) * 0.06).bfloat16().float().contiguous()
+    bias = (torch.randn(64, device="cuda", generator=g) * 0.1).contiguous()
+    pooled = torch.empty(B, H // 2, W // 2, 64, device="cuda")
+    codes = torch.zeros(B, H // 2, W // 2, 8, device="cuda", dtype=torch.int32)
+    scratch = torch.empty(udh.L.udh_debug_tc_conv_scratch_bytes(B, H, W, 64, 64), device="cuda", dtype=torch.uint8)
+    assert udh.L.udh_debug_tc_conv_pool(P(x), P(w), P(bias), P(pooled), P(codes), P(scratch), B, H, W, None) == 0, udh.L.udh_last_error()
+    torch.cuda.synchronize()
+    full = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), bias, padding=1))   # [B,64,H,W]
+    ref = torch.nn.functional.max_pool2d(full, 2).permute(0, 2, 3, 1)
+    tol = 1e-2 * ref.abs().max().item()
+    assert (pooled - ref).abs().max().item() <= tol
+    # decode the codes: channel c of pooled pixel -> 3 bits at (c % 8) * 3 of word c // 8
+    sh = (torch.arange(64, device="cuda") % 8) * 3
+    k = (codes.long()[..., torch.arange(64, device="cuda") // 8] >> sh) & 7                  # [B,H/2,W/2,64]
+    assert int(k.max()) <= 4
+    win = full.permute(0, 2, 3, 1).reshape(B, H // 2, 2, W // 2, 2, 64).permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, 64, 4)
+    picked = torch.gather(win, 4, k.clamp(max=3).unsqueeze(-1)).squeeze(-1)
+    live = k < 4
+    assert (picked[live] - ref[live]).abs().max().item() <= tol
+    assert ref[~live].abs().max().item() <= tol if (~live).any() else True
+    assert (ref[live] > -tol).all()
+    assert live.float().mean().item() > 0.5

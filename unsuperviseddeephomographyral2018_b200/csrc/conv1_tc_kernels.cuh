@@ -52,8 +52,10 @@ __device__ __forceinline__ void build_im2col_row(uint8_t* tile, int r, const flo
 }
 
 // ------------------------------------------------------------------------------------------------------------- forward
-// 160 threads: warps 0-3 workers (thread = pixel = TMEM lane), warp 4 = TMEM alloc + MMA issuer.
-__global__ void __launch_bounds__(160, 1)
+// 160 threads: warps 0-3 workers (thread = pixel = TMEM lane), warp 4 = TMEM alloc + MMA issuer.  The workers are
+// instruction-bound (im2col build + 64-channel epilogue per pixel), so several CTAs share an SM (kConv1CtasPerSm).
+constexpr int kConv1CtasPerSm = 3;
+__global__ void __launch_bounds__(160, kConv1CtasPerSm)
 conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g, const float* __restrict__ I1,
                     const float* __restrict__ I2, const float* __restrict__ w, const float* __restrict__ bias,
                     uint32_t* __restrict__ mask_out) {
@@ -189,7 +191,7 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
 
 // ------------------------------------------------------------------------------------------------------------- wgrad
 // 160 threads: warps 0-3 build im2col tiles (+ the constant-one column 18), warp 4 = TMA (G rows) + TMEM alloc + MMA issuer.
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, kConv1CtasPerSm)
 conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g, const float* __restrict__ I1,
                       const float* __restrict__ I2, float* __restrict__ dW, float* __restrict__ db) {
   extern __shared__ uint8_t raw[];

@@ -216,11 +216,11 @@ __global__ void pool_bwd_bf16_kernel(const uint32_t* __restrict__ codes, const _
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
-template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI>
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, bool POOL = false>
 int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                      const tc::ConvGeom& g, const float* bias, const __nv_bfloat16* mask_src, const uint32_t* mask_bits,
                      uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, size_t smem, cudaStream_t st) {
-  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI>;
+  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI, POOL>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
@@ -262,6 +262,29 @@ int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* b
                                                      smem, st);
 }
 
+// conv (64 -> 64, W == 128) + bias + ReLU + 2x2 max-pool in one kernel: writes the pooled padded stream and the routing codes
+int tc_conv_pool(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, __nv_bfloat16* pooled, uint32_t* codes, int B, int H,
+                 int W, cudaStream_t st) {
+  UDH_REQUIRE(W == 128 && H % 2 == 0, "tc_conv_pool: needs W == 128 and an even height (got %d x %d)", H, W);
+  tc::ConvGeom g;
+  g.B = B; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
+  g.Q = B * g.Hp * g.Wp;
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  g.num_items = B * (H / 2);
+  g.abuf_rows = 2 * 128 + 2 * g.hh;
+  UDH_REQUIRE(g.hh + g.Wp + 128 + g.Wp + 1 <= g.abuf_rows, "tc_conv_pool: halo does not cover the second row tile");
+  CUtensorMap tmA128, tmAhh, tmW;
+  uint64_t dimsA[2] = {64, (uint64_t)g.Q}, strA[2] = {2, 128};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh};
+  TRY(tc::make_tmap_bf16(&tmA128, x, 2, dimsA, strA, box128));
+  TRY(tc::make_tmap_bf16(&tmAhh, x, 2, dimsA, strA, boxhh));
+  uint64_t dimsW[2] = {64, (uint64_t)9 * 64}, strW[2] = {2, 128};
+  uint32_t boxW[2] = {64, 64};
+  TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
+  const size_t smem = tc::ConvSmem<64, 1, 2, true>::bytes(g.abuf_rows, false);
+  return launch_conv_impl<64, 1, 2, true, false, true>(tmA128, tmAhh, tmW, tmW, g, bias, nullptr, nullptr, codes, pooled, nullptr, 1, smem, st);
+}
+
 // one 3x3 conv on padded bf16 streams; (cin -> cout) selects the kernel instance
 int tc_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const __nv_bfloat16* mask_src,
             const uint32_t* mask_bits, uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, int B, int H, int W, int cin,
@@ -284,7 +307,7 @@ int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, c
   pad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
   return check_launch("pad_cast");
 }
-[[maybe_unused]] int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
+int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * H * W * (C / 4);
   unpad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
   return check_launch("unpad_cast");
@@ -404,7 +427,8 @@ int conv1_tc_fwd(const float* I1, const float* I2, const float* w, const float* 
   TRY(tc::make_tmap_bf16(&tmOut, out_pad, 2, dims, str, box));
   const size_t smem = 1024 + 2 * 16384 + 8192 + 16384 + 256;
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = g.tiles < 2 * persistent_ctas() ? g.tiles : 2 * persistent_ctas();
+  const int want = tc::kConv1CtasPerSm * persistent_ctas();
+  const int grid = g.tiles < want ? g.tiles : want;
   tc::conv1_tc_fwd_kernel<<<grid, 160, smem, st>>>(tmOut, g, I1, I2, w, bias, mask_out);
   return check_launch("conv1_tc_fwd_kernel");
 }
@@ -420,7 +444,8 @@ int conv1_tc_wgrad(const float* I1, const float* I2, const __nv_bfloat16* G_pad,
   TRY(tc::make_tmap_bf16(&tmG, G_pad, 2, dims, str, box));
   const size_t smem = 1024 + 4 * 16384 + 256;
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = g.tiles < 2 * persistent_ctas() ? g.tiles : 2 * persistent_ctas();
+  const int want = tc::kConv1CtasPerSm * persistent_ctas();
+  const int grid = g.tiles < want ? g.tiles : want;
   tc::conv1_tc_wgrad_kernel<<<grid, 160, smem, st>>>(tmG, g, I1, I2, dW, db);
   return check_launch("conv1_tc_wgrad_kernel");
 }
@@ -465,15 +490,22 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
     ProfScope ps(PROF_CONV_FWD0, st);
     TRY(conv1_tc_fwd(I1, I2, params + poff[0], params + poff[1], Pb(0), reinterpret_cast<uint32_t*>(tcw + L.Mb[0]), B, P, P, st));
   }
+  const bool fuse_pool1 = (P == 128);      // conv1_2 + pool1 in one kernel (its row tiling needs 128-wide images)
   for (int i = 1; i < 8; ++i) {
     const int s = P / kConv[i].div;
+    if (i == 1 && fuse_pool1) {
+      ProfScope ps(PROF_CONV_FWD0 + i, st);
+      TRY(tc_conv_pool(Pb(0), reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[1]), params + poff[3], Pb(8),
+                       reinterpret_cast<uint32_t*>(tcw + L.Px[0]), B, s, s, st));
+      continue;
+    }
     {
       ProfScope ps(PROF_CONV_FWD0 + i, st);
       TRY(tc_conv(Pb(input_of(i)), reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]), params + poff[2 * i + 1], nullptr, nullptr,
                   (i % 2 == 0) ? reinterpret_cast<uint32_t*>(tcw + L.Mb[i]) : nullptr, Pb(i),
                   i == 7 ? at<float>(ws, act_off[7]) : nullptr, 1, B, s, s, kConv[i].cin, kConv[i].cout, st));
     }
-    if (i == 1 || i == 3 || i == 5) {
+    if ((i == 3 || i == 5) || (i == 1 && !fuse_pool1)) {
       ProfScope ps(PROF_POOL_FWD, st);
       TRY(pool_fwd_bf16(Pb(i), Pb(8 + i / 2), reinterpret_cast<uint32_t*>(tcw + L.Px[i / 2]), B, s, s, kConv[i].cout, st));
     }
@@ -576,6 +608,22 @@ int tc_debug_conv(const float* x, const float* w, const float* bias, float* out,
   return UDH_OK;
 }
 
+// Debug / test entry: fused conv (64 -> 64) + bias + ReLU + 2x2 max-pool.  x [B,H,128,64] fp32 -> pooled [B,H/2,64,64] fp32 and
+// routing codes [B,H/2,64,8] uint32 (3 bits per channel: 0..3 = winner in scan order, 4 = maximum not positive).
+int tc_debug_conv_pool(const float* x, const float* w, const float* bias, float* pooled, uint32_t* codes, void* scratch, int B, int H, int W,
+                       cudaStream_t st) {
+  char* s = reinterpret_cast<char*>(scratch);
+  const size_t in_bytes = al256((size_t)B * (H + 2) * (W + 2) * 64 * 2);
+  __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(s);
+  __nv_bfloat16* pp = reinterpret_cast<__nv_bfloat16*>(s + in_bytes);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(s + 2 * in_bytes);
+  UDH_CUDA(cudaMemsetAsync(scratch, 0, tc_debug_scratch_bytes(B, H, W, 64, 64), st));
+  TRY(pad_cast(x, xp, B, H, W, 64, st));
+  TRY(pack_weights(w, wp, 64, 64, 0, st));
+  TRY(tc_conv_pool(xp, wp, bias, pp, codes, B, H, W, st));
+  return unpad_cast(pp, pooled, B, H / 2, W / 2, 64, st);
+}
+
 // Debug / test entry: tensor-core weight gradient on fp32 NHWC tensors x [B,H,W,cin], g [B,H,W,cout] -> dW HWIO, db (accumulated).
 int tc_debug_wgrad(const float* x, const float* gsrc, float* dW, float* db, void* scratch, int B, int H, int W, int cin, int cout,
                    cudaStream_t st) {
@@ -594,6 +642,12 @@ extern "C" int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, flo
                                   int cout, void* stream) {
   UDH_REQUIRE(x && g && dW && scratch, "udh_debug_tc_wgrad: null pointer");
   return udh::tc_debug_wgrad(x, g, dW, db, scratch, B, H, W, cin, cout, udh::as_stream(stream));
+}
+
+extern "C" int udh_debug_tc_conv_pool(const float* x, const float* w, const float* bias, float* pooled, uint32_t* codes, void* scratch,
+                                      int B, int H, int W, void* stream) {
+  UDH_REQUIRE(x && w && bias && pooled && codes && scratch, "udh_debug_tc_conv_pool: null pointer");
+  return udh::tc_debug_conv_pool(x, w, bias, pooled, codes, scratch, B, H, W, udh::as_stream(stream));
 }
 
 extern "C" size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout) {

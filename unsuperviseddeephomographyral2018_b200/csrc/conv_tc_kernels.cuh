@@ -15,6 +15,13 @@
 //   * fp32 accumulators live in TMEM (2 sets x T tiles x Cout columns): the epilogue warps drain set b while the MMA
 //     thread fills set b^1 and the TMA thread prefetches the next item's rows.
 //   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: epilogue (TMEM lane quarters).
+//
+// POOL variant (W == 128, T == 2, Cout == 64: conv1_2).  An item is the interior of two consecutive image rows
+// (2y, 2y+1): tile t starts at the first interior position of row 2y+t, i.e. the two tiles are Wp (not 128) rows apart in
+// the same staged buffer, no border position is computed, and the epilogue thread of column x holds both rows of that
+// column.  It applies bias + ReLU, takes the 2x2 maximum (vertical in registers, horizontal with one lane exchange) and
+// writes the POOLED padded stream plus the 3-bit routing codes of the max-pool backward — the full-resolution
+// activation is never written or re-read.
 #pragma once
 #include "tc_common.cuh"
 
@@ -45,7 +52,7 @@ struct ConvSmem {
 // TMA_EPI: the epilogue stages each warp's 32 x 64-channel bf16 block in (swizzled) shared memory and writes it with one
 // TMA store (full 128-byte lines, asynchronous); the ReLU-mask block of a dgrad is fetched the same way round (coalesced
 // 512-byte warp loads into the staging block).  Without it each lane stores its own 64 bytes at a 128-byte stride.
-template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI>
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, bool POOL = false>
 __global__ void __launch_bounds__(256, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
@@ -98,7 +105,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       auto load_item = [&](int it) {
         const int b = it & 1;
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int q0 = item * T * 128;
+        const int q0 = POOL ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 : item * T * 128;
         mbar_wait(&a_empty[b], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&a_full[b], (uint32_t)(CB * abuf_bytes));
         for (int cb = 0; cb < CB; ++cb) {
@@ -129,6 +136,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
     const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
     if (WRES) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
+    const uint32_t tile_step = POOL ? (uint32_t)g.Wp * 8 : 1024u;   // 16-byte units between the tiles of an item
     uint32_t wcount = 0;
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
@@ -157,8 +165,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
 #pragma unroll
           for (int t = 0; t < T; ++t) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)     // +1024 (16-byte units) per 128-row tile, +2 per 32-byte k-step
-              umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
+            for (int k = 0; k < 4; ++k)     // +tile_step (16-byte units) per tile, +2 per 32-byte k-step
+              umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * tile_step + k * 2), desc_from_lo(w_lo + k * 2), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
           if (!WRES) umma_commit(&w_empty[s]);
@@ -174,7 +182,59 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
-    if (TMA_EPI) {
+    if constexpr (POOL) {
+      static_assert(!POOL || (N_OUT == 64 && T == 2 && CB == 1), "POOL variant: 64 -> 64 channels, two row tiles");
+      const int ew = warp - 4;
+      const int OH = g.H >> 1, OW = g.W >> 1;
+      const int x = ew * 32 + lane;                 // column of this thread (W == 128 == tile rows)
+      const int px = x >> 1, odd = x & 1;
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int n = item / OH, yy = item - n * OH;
+        mbar_wait(&t_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        __nv_bfloat16* prow = out_bf + (((size_t)n * (OH + 2) + yy + 1) * (OW + 2) + px + 1) * 64;
+        uint32_t* crow = mask_out + (((size_t)n * OH + yy) * OW + px) * 8;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float v0[32], v1[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + 0) * 64 + c * 32), v0);
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + 1) * 64 + c * 32), v1);
+          uint32_t code[4] = {0u, 0u, 0u, 0u};
+          float m[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float bj = __ldg(bias + c * 32 + j);
+            const float a = fmaxf(v0[j] + bj, 0.f), d = fmaxf(v1[j] + bj, 0.f);
+            // scan order of the 2x2 window: (row 0, x even)=0, (row 0, x odd)=1, (row 1, even)=2, (row 1, odd)=3;
+            // the first maximum wins: larger value, ties to the smaller index
+            float vs = a; uint32_t ks = (uint32_t)odd;
+            if (d > a) { vs = d; ks = 2u + (uint32_t)odd; }
+            const float vo = __shfl_xor_sync(0xffffffffu, vs, 1);
+            const uint32_t ko = __shfl_xor_sync(0xffffffffu, ks, 1);
+            const bool other = vo > vs || (vo == vs && ko < ks);
+            const float mv = other ? vo : vs;
+            const uint32_t mk = other ? ko : ks;
+            m[j] = mv;
+            code[j >> 3] |= (mv > 0.f ? mk : 4u) << (3 * (j & 7));
+          }
+          // both lanes of a pair hold the pooled pixel: the even lane stores channels 0-15 of this chunk, the odd 16-31
+          uint32_t pk[8];
+#pragma unroll
+          for (int h = 0; h < 8; ++h) {
+            const __nv_bfloat162 p = __floats2bfloat162_rn(odd ? m[16 + 2 * h] : m[2 * h], odd ? m[17 + 2 * h] : m[2 * h + 1]);
+            pk[h] = *reinterpret_cast<const uint32_t*>(&p);
+          }
+          uint4* op = reinterpret_cast<uint4*>(prow + c * 32 + odd * 16);
+          op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          *reinterpret_cast<uint2*>(crow + c * 4 + odd * 2) = odd ? make_uint2(code[2], code[3]) : make_uint2(code[0], code[1]);
+        }
+        tc_fence_before();
+        mbar_arrive(&t_empty[b]);
+      }
+    } else if (TMA_EPI) {
       const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
       const int HpWp = g.Hp * g.Wp;
       uint8_t* stg = sEpi + ew * 4096;              // this warp's 32 x 128 B staging block (1024-byte aligned)

@@ -22,7 +22,7 @@ struct GemmGeom {
 constexpr int kGemmStages = 4;
 constexpr int kGemmStageBytes = 16384 + 32768;   // A 128 x 64, B 256 x 64 (bf16)
 
-constexpr int kGemmEpiBytes = 4 * 32 * 128;      // TMA-store staging of the non-atomic epilogue: 32 rows x 32 floats per warp
+constexpr int kGemmEpiBytes = 2 * 4 * 32 * 128;  // TMA-store staging of the non-atomic epilogue: 2 x (32 rows x 32 floats) per warp
 
 // ATOMIC: split-K partial tiles are added with 16-byte vector reductions.  Otherwise the tile is stored through a swizzled
 // shared-memory staging block and TMA (full 128-byte lines; rows / columns beyond M / N are clipped by the tensor map).
@@ -115,10 +115,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     const int ew = warp - 4;
-    uint8_t* stg = sEpi + ew * 4096;
-    const uint32_t my_row = smem_u32(stg) + lane * 128;
-    const int sw = lane & 7;
-    bool store_pending = false;
+    uint8_t* stg0 = sEpi + ew * 8192;            // two staging blocks per warp: chunk c fills one while the TMA store
+    const int sw = lane & 7;                      // of chunk c-1 still reads the other
+    int stores_in_flight = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
       int mt, nt, ks;
@@ -144,15 +143,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
+          uint8_t* stg = stg0 + (c & 1) * 4096;
+          const uint32_t my_row = smem_u32(stg) + lane * 128;
+          if (stores_in_flight >= 2) { if (lane == 0) bulk_wait_read1(); __syncwarp(); stores_in_flight = 1; }
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4)
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)((j4 ^ sw) << 4)), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]),
                          "f"(v[4 * j4 + 2]), "f"(v[4 * j4 + 3]) : "memory");
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0 && n0 < g.N && mt * 128 + ew * 32 < g.M) { tma_store_2d(&tmC, stg, n0, mt * 128 + ew * 32); bulk_commit(); }
-          store_pending = true;
+          if (lane == 0) {                          // (always commit, possibly an empty group, so the group count stays uniform)
+            if (n0 < g.N && mt * 128 + ew * 32 < g.M) tma_store_2d(&tmC, stg, n0, mt * 128 + ew * 32);
+            bulk_commit();
+          }
+          ++stores_in_flight;
         }
       }
       tc_fence_before();
