@@ -360,10 +360,36 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   return check_launch("tc_wgrad_kernel");
 }
 
+// 64 -> 64 layers: the N = 192 kernel (see wgrad_tc_kernels.cuh)
+int launch_wgrad64(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float* db, int B, int H, int W, cudaStream_t st) {
+  constexpr int T = 2;
+  tc::Wgrad64Geom g;
+  g.Wp = W + 2;
+  g.Q = B * (H + 2) * (W + 2);
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  const int tiles = (g.Q + 127) / 128;
+  g.num_items = (tiles + T - 1) / T;
+  g.xrows = T * 128 + 2 * g.hh;
+  CUtensorMap tmX128, tmXhh, tmG136;
+  uint64_t dims[2] = {64, (uint64_t)g.Q}, str[2] = {2, 128};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh}, box136[2] = {64, 136};
+  TRY(tc::make_tmap_bf16(&tmX128, x, 2, dims, str, box128));
+  TRY(tc::make_tmap_bf16(&tmXhh, x, 2, dims, str, boxhh));
+  TRY(tc::make_tmap_bf16(&tmG136, gsrc, 2, dims, str, box136));
+  const size_t stage = (size_t)g.xrows * 128 + (size_t)(T * 128 + 16) * 128;
+  const size_t smem = 1024 + 2 * stage + 16384 + 256;
+  UDH_REQUIRE(smem <= 232448, "tc wgrad64: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+  auto kern = tc::tc_wgrad64_kernel<T>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = persistent_ctas();
+  kern<<<g.num_items < sms ? g.num_items : sms, 256, smem, st>>>(tmX128, tmXhh, tmG136, g, dW, db);
+  return check_launch("tc_wgrad64_kernel");
+}
+
 // dW (HWIO fp32) += X^T-shifted . G ; db += sum G   for one layer, on padded bf16 streams
 int tc_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float* db, int B, int H, int W, int cin, int cout,
              cudaStream_t st) {
-  if (cin == 64 && cout == 64) return launch_wgrad<64, 1, 2>(x, gsrc, dW, db, B, H, W, st);
+  if (cin == 64 && cout == 64) return launch_wgrad64(x, gsrc, dW, db, B, H, W, st);
   if (cin == 64 && cout == 128) return launch_wgrad<128, 1, 1>(x, gsrc, dW, db, B, H, W, st);
   if (cin == 128 && cout == 128) return launch_wgrad<128, 2, 1>(x, gsrc, dW, db, B, H, W, st);
   set_error("tc_wgrad: unsupported channel combination %d -> %d", cin, cout);

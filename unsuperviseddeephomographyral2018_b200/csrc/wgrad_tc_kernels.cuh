@@ -185,5 +185,141 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 64 -> 64 channel layers (conv1_2, conv2_1, conv2_2): N = 192 variant.
+// An (M128, N64, K16) MMA is capped at ~50 clk by the rate at which the 4 KB A operand can be fetched from shared memory
+// (64 % of the tensor peak, measured with tools/tc_probe2.py; pairing CTAs does not change it), so here the N side is
+// widened instead: B is THREE row shifts of the gradient rows, c = -1, 0, +1 (three 64-wide MN blocks, leading-dimension
+// byte offset = one 128-byte row), A is two row shifts of X (ky and ky' rows of the 3x3 window, as above).  Since
+//   sum_q X[q + a][ci] * G[q + c][co]  =  dW at tap offset (a - c),
+// one (M128, N192, K16) MMA yields the six taps (ky, ky') x (kx = -c), and the whole 3x3 window + bias gradient takes
+// TWO MMAs per 16 positions (96 clk each) instead of five (50 clk each):
+//   group 0: A = X[q - Wp] | X[q]          -> taps ky = -1, 0 ; kx = +1, 0, -1 (N blocks 0, 1, 2)
+//   group 1: A = X[q + Wp] | ones          -> taps ky = +1    ; rows 64.. = bias gradient (taken from N block 1)
+// G needs one halo row on each side (8 are staged to keep the 1024-byte swizzle-atom alignment of the TMA boxes).
+struct Wgrad64Geom {
+  int Wp, Q, hh;
+  int num_items;     // ceil(ceil(Q/128) / T)
+  int xrows;         // T*128 + 2*hh
+};
+
+template <int T>
+__global__ void __launch_bounds__(256, 1)
+tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constant__ CUtensorMap tmXhh,
+                  const __grid_constant__ CUtensorMap tmG136, const Wgrad64Geom g, float* __restrict__ dW, float* __restrict__ db) {
+  static_assert(T == 2, "G is staged as two 136-row boxes");
+  extern __shared__ uint8_t raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  const int xblk_bytes = g.xrows * 128;
+  constexpr int kGRows = T * 128 + 16;                          // 8 halo rows on each side
+  constexpr int gblk_bytes = kGRows * 128;
+  const int stage_bytes = xblk_bytes + gblk_bytes;
+  uint8_t* sStage = base;                                       // [2][ X rows | G rows ]
+  uint8_t* sOnes = base + 2 * (size_t)stage_bytes;              // [128][64] bf16 ones
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 16384);
+  uint64_t* full = bars;        // [2]
+  uint64_t* empty = bars + 2;   // [2]
+  uint64_t* acc_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmemCols = 512;                                // 2 groups x 192 columns
+
+  {
+    uint32_t* o = reinterpret_cast<uint32_t*>(sOnes);
+    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) o[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmX128); prefetch_tmap(&tmXhh); prefetch_tmap(&tmG136); }
+  if (warp == 2) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int my_items = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int s = it & 1;
+        const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * T * 128;
+        mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)stage_bytes);
+        uint8_t* dst = sStage + (size_t)s * stage_bytes;
+        tma_load_2d(dst, &tmXhh, 0, q0 - g.hh, &full[s]);
+        for (int t = 0; t < T; ++t) tma_load_2d(dst + (size_t)(g.hh + t * 128) * 128, &tmX128, 0, q0 + t * 128, &full[s]);
+        tma_load_2d(dst + (size_t)(g.hh + T * 128) * 128, &tmXhh, 0, q0 + T * 128, &full[s]);
+        uint8_t* gd = dst + xblk_bytes;
+        tma_load_2d(gd, &tmG136, 0, q0 - 8, &full[s]);
+        tma_load_2d(gd + 136 * 128, &tmG136, 0, q0 + 128, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 192, 1, 1);
+    const uint32_t ones_addr = smem_u32(sOnes);
+    for (int it = 0; it < my_items; ++it) {
+      const int s = it & 1;
+      mbar_wait(&full[s], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t x_addr = smem_u32(sStage + (size_t)s * stage_bytes);
+      const uint32_t g_addr = x_addr + (uint32_t)xblk_bytes;
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const uint32_t b_lo = desc_lo(g_addr + (uint32_t)(8 + t * 128 - 1) * 128, 128);     // G[q-1] | G[q] | G[q+1]
+#pragma unroll
+        for (int gl = 0; gl < 2; ++gl) {
+          const uint32_t a_start = x_addr + (uint32_t)(g.hh + t * 128 + (gl == 0 ? -g.Wp : g.Wp)) * 128;
+          const uint32_t lbo = gl == 0 ? (uint32_t)g.Wp * 128 : ones_addr - a_start;
+          const uint32_t a_lo = desc_lo(a_start, lbo);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(gl * 192);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16(d_tmem, desc_from_lo(a_lo + kk * 128), desc_from_lo(b_lo + kk * 128), idesc, (it > 0 || t > 0 || kk > 0) ? 1u : 0u);
+          }
+          __syncwarp();
+        }
+      }
+      if (elect_one()) umma_commit(&empty[s]);
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+  } else if (warp >= 4 && my_items > 0) {
+    const int ew = warp - 4;
+    const int m = ew * 32 + lane;
+    const int ci = m & 63;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int gl = 0; gl < 2; ++gl) {
+      const int ky = gl == 0 ? (m >> 6) - 1 : 1;                  // rows 64.. of group 1 are the ones rows
+      const bool is_ones = gl == 1 && m >= 64;
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) {
+        const int j = c >> 1;                                     // N block: G shift c = j - 1  ->  kx = 1 - j
+        const int tap = (ky + 1) * 3 + (2 - j);
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(gl * 192 + c * 32), v);
+        float* dst = is_ones ? db : dW + ((size_t)tap * 64 + ci) * 64;
+        const bool active = is_ones ? (m == 64 && j == 1 && db != nullptr) : true;
+        if (active) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            red_add_v4(dst + (c & 1) * 32 + 4 * jj, v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
 }  // namespace tc
 }  // namespace udh
