@@ -64,7 +64,11 @@ inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cas
 // ---------------------------------------------------------------------------------------------------- small kernels
 // dst[tap][cb][n][k] bf16 <- fp32 HWIO w[tap][ci][co].
 //   forward: n = co, k-channel = ci.   dgrad: n = ci, k-channel = co, tap mirrored (w[8-tap]).
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cin, int Cout, int dgrad) {
+// rowtile != 0: block p of dst holds tap (ky, kx) = (2 - p % 3, p / 3), i.e. for every kx the three ky taps are adjacent in
+// the order +1, 0, -1 — the row-tile conv kernels read two adjacent blocks as one N = 128 operand.
+__device__ __forceinline__ int packed_src_tap(int p, int rowtile) { return rowtile ? (2 - p % 3) * 3 + p / 3 : p; }
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cin, int Cout, int dgrad, int rowtile) {
   const int K = dgrad ? Cout : Cin, N = dgrad ? Cin : Cout;      // contraction channels, output channels of the packed conv
   const int CBk = K / 64;
   const int total = 9 * K * N;
@@ -73,7 +77,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     int r = i >> 6;
     const int n = r % N; r /= N;
     const int cb = r % CBk;
-    const int tap = r / CBk;
+    const int tap = packed_src_tap(r / CBk, rowtile);
     const int kc = cb * 64 + k;
     const float v = dgrad ? w[((size_t)(8 - tap) * Cin + n) * Cout + kc] : w[((size_t)tap * Cin + kc) * Cout + n];
     dst[i] = __float2bfloat16_rn(v);
@@ -81,7 +85,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 // all seven tensor-core layers in one launch (both directions): blockIdx.y = layer-1, blockIdx.z = direction
-struct PackTable { const float* w[7]; __nv_bfloat16* fwd[7]; __nv_bfloat16* dgr[7]; int cin[7], cout[7]; };
+struct PackTable { const float* w[7]; __nv_bfloat16* fwd[7]; __nv_bfloat16* dgr[7]; int cin[7], cout[7]; int rowtile_fwd[7], rowtile_dgr[7]; };
 __global__ void pack_all_weights_kernel(PackTable t, int do_fwd, int do_dgrad) {
   const int L = blockIdx.y, dgrad = blockIdx.z;
   if ((dgrad && !do_dgrad) || (!dgrad && !do_fwd)) return;
@@ -94,7 +98,7 @@ __global__ void pack_all_weights_kernel(PackTable t, int do_fwd, int do_dgrad) {
     int r = i >> 6;
     const int n = r % N; r /= N;
     const int cb = r % CBk;
-    const int tap = r / CBk;
+    const int tap = packed_src_tap(r / CBk, dgrad ? t.rowtile_dgr[L] : t.rowtile_fwd[L]);
     const int kc = cb * 64 + k;
     dst[i] = __float2bfloat16_rn(dgrad ? w[((size_t)(8 - tap) * Cin + n) * Cout + kc] : w[((size_t)tap * Cin + kc) * Cout + n]);
   }
@@ -216,11 +220,11 @@ __global__ void pool_bwd_bf16_kernel(const uint32_t* __restrict__ codes, const _
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
-template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, bool POOL = false>
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, int ROWS = 0>
 int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const CUtensorMap& tmW, const CUtensorMap& tmOut,
                      const tc::ConvGeom& g, const float* bias, const __nv_bfloat16* mask_src, const uint32_t* mask_bits,
                      uint32_t* mask_out, __nv_bfloat16* out_bf, float* out_f32, int relu, size_t smem, cudaStream_t st) {
-  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI, POOL>;
+  auto kern = tc::tc_conv_kernel<N_OUT, CB, T, WRES, TMA_EPI, ROWS>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
@@ -282,7 +286,33 @@ int tc_conv_pool(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* 
   uint32_t boxW[2] = {64, 64};
   TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
   const size_t smem = tc::ConvSmem<64, 1, 2, true>::bytes(g.abuf_rows, false);
-  return launch_conv_impl<64, 1, 2, true, false, true>(tmA128, tmAhh, tmW, tmW, g, bias, nullptr, nullptr, codes, pooled, nullptr, 1, smem, st);
+  return launch_conv_impl<64, 1, 2, true, false, 1>(tmA128, tmAhh, tmW, tmW, g, bias, nullptr, nullptr, codes, pooled, nullptr, 1, smem, st);
+}
+
+// conv (64 -> 64, W == 128) on row tiles with the plain epilogue (bias / ReLU / 1-bit mask / TMA store); weights must be
+// packed in row-tile block order.  Used for the dgrad of conv1_2.
+int tc_conv_rows(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out,
+                 __nv_bfloat16* out_bf, int relu, int B, int H, int W, cudaStream_t st) {
+  UDH_REQUIRE(W == 128 && H % 2 == 0 && out_bf, "tc_conv_rows: needs W == 128, an even height and an output stream");
+  tc::ConvGeom g;
+  g.B = B; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
+  g.Q = B * g.Hp * g.Wp;
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  g.num_items = B * (H / 2);
+  g.abuf_rows = 2 * 128 + 2 * g.hh;
+  UDH_REQUIRE(g.hh + g.Wp + 128 + g.Wp + 1 <= g.abuf_rows, "tc_conv_rows: halo does not cover the second row tile");
+  CUtensorMap tmA128, tmAhh, tmW, tmOut;
+  uint64_t dimsA[2] = {64, (uint64_t)g.Q}, strA[2] = {2, 128};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh}, boxO[2] = {64, 32};
+  TRY(tc::make_tmap_bf16(&tmA128, x, 2, dimsA, strA, box128));
+  TRY(tc::make_tmap_bf16(&tmAhh, x, 2, dimsA, strA, boxhh));
+  uint64_t dimsW[2] = {64, (uint64_t)9 * 64}, strW[2] = {2, 128};
+  uint32_t boxW[2] = {64, 64};
+  TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
+  TRY(tc::make_tmap_bf16(&tmOut, out_bf, 2, dimsA, strA, boxO));
+  const size_t smem = tc::ConvSmem<64, 1, 2, true>::bytes(g.abuf_rows, true);
+  UDH_REQUIRE(smem <= 232448, "tc_conv_rows: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+  return launch_conv_impl<64, 1, 2, true, true, 2>(tmA128, tmAhh, tmW, tmOut, g, bias, nullptr, mask_bits, mask_out, out_bf, nullptr, relu, smem, st);
 }
 
 // one 3x3 conv on padded bf16 streams; (cin -> cout) selects the kernel instance
@@ -297,9 +327,9 @@ int tc_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* bias,
   return UDH_ENOSUP;
 }
 
-int pack_weights(const float* w, __nv_bfloat16* dst, int cin, int cout, int dgrad, cudaStream_t st) {
+int pack_weights(const float* w, __nv_bfloat16* dst, int cin, int cout, int dgrad, cudaStream_t st, int rowtile = 0) {
   const int total = 9 * cin * cout;
-  pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, dst, cin, cout, dgrad);
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, dst, cin, cout, dgrad, rowtile);
   return check_launch("pack_weights");
 }
 int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, cudaStream_t st) {
@@ -507,6 +537,8 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
       t.fwd[i - 1] = reinterpret_cast<__nv_bfloat16*>(tcw + L.wf[i]);
       t.dgr[i - 1] = reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[i]);
       t.cin[i - 1] = kConv[i].cin; t.cout[i - 1] = kConv[i].cout;
+      t.rowtile_fwd[i - 1] = (i == 1 && P == 128) ? 1 : 0;          // conv1_2 forward runs on row tiles (fused with pool1)
+      t.rowtile_dgr[i - 1] = (i == 1 && P == 128) ? 1 : 0;          // ... and so does its dgrad
     }
     pack_all_weights_kernel<<<dim3(72, 7, 2), 256, 0, st>>>(t, 1, 1);
     TRY(check_launch("pack_all_weights"));
@@ -564,6 +596,13 @@ int tc_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     if (i == 0) break;
     const bool below_is_pool = (i == 2 || i == 4 || i == 6);
     const int below = input_of(i);
+    if (i == 1 && P == 128) {
+      // conv1_2 dgrad on row tiles (weights were packed in row-tile order by the forward), ReLU mask of conv1_1 fused
+      ProfScope ps(PROF_CONV_DGRAD0 + i, st);
+      TRY(tc_conv_rows(Gb(1), reinterpret_cast<__nv_bfloat16*>(tcw + L.wd[1]), nullptr, reinterpret_cast<const uint32_t*>(tcw + L.Mb[0]),
+                       nullptr, Gb(0), 0, B, s, s, st));
+      continue;
+    }
     {
       ProfScope ps(PROF_CONV_DGRAD0 + i, st);
       // dgrad = conv of G[i] with the mirrored kernel; ReLU mask of the layer below fused unless a pool sits between
@@ -645,7 +684,7 @@ int tc_debug_conv_pool(const float* x, const float* w, const float* bias, float*
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(s + 2 * in_bytes);
   UDH_CUDA(cudaMemsetAsync(scratch, 0, tc_debug_scratch_bytes(B, H, W, 64, 64), st));
   TRY(pad_cast(x, xp, B, H, W, 64, st));
-  TRY(pack_weights(w, wp, 64, 64, 0, st));
+  TRY(pack_weights(w, wp, 64, 64, 0, st, 1));
   TRY(tc_conv_pool(xp, wp, bias, pp, codes, B, H, W, st));
   return unpad_cast(pp, pooled, B, H / 2, W / 2, 64, st);
 }

@@ -16,12 +16,19 @@
 //     thread fills set b^1 and the TMA thread prefetches the next item's rows.
 //   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: epilogue (TMEM lane quarters).
 //
-// POOL variant (W == 128, T == 2, Cout == 64: conv1_2).  An item is the interior of two consecutive image rows
-// (2y, 2y+1): tile t starts at the first interior position of row 2y+t, i.e. the two tiles are Wp (not 128) rows apart in
-// the same staged buffer, no border position is computed, and the epilogue thread of column x holds both rows of that
-// column.  It applies bias + ReLU, takes the 2x2 maximum (vertical in registers, horizontal with one lane exchange) and
-// writes the POOLED padded stream plus the 3-bit routing codes of the max-pool backward — the full-resolution
-// activation is never written or re-read.
+// Row-tile variants (W == 128, T == 2, 64 -> 64 channels: conv1_2).  ROWS = 1: forward fused with pool1; ROWS = 2: dgrad
+// with the plain bias / mask / TMA-store epilogue.  An item is the interior of two consecutive image rows (2y, 2y+1):
+// tile t starts at the first interior position of row 2y+t, i.e. the two tiles are Wp (not 128) rows apart in the same
+// staged buffer, no border position is computed, and the epilogue thread of column x holds both rows of that column.
+//   * ROWS = 1 epilogue: bias + ReLU, 2x2 maximum (vertical in registers, horizontal with one lane exchange), then the
+//     POOLED padded stream plus the 3-bit routing codes of the max-pool backward are written — the full-resolution
+//     activation is never written or re-read.
+//   * MMA schedule: a vertical tap is exactly one tile here, so the MMAs are organised by INPUT row instead of output
+//     row.  Input row r feeds output rows r-1, r, r+1 through the ky = +1, 0, -1 weights; for one kx the input rows
+//     2y-1 .. 2y+2 issue (N64 | N128 | N128 | N64) MMAs whose N = 128 operands are two adjacent weight blocks writing the
+//     two adjacent accumulators at once: 4 k-steps x (50 + 64 + 64 + 50) clk instead of 6 x 50 per kx — the
+//     A-fetch-bound N = 64 rate (tools/tc_probe2.py) applies to half of the MMAs only.  Weights are packed in
+//     (kx, ky descending) block order (pack_weights_kernel, rowtile = 1).
 #pragma once
 #include "tc_common.cuh"
 
@@ -52,12 +59,14 @@ struct ConvSmem {
 // TMA_EPI: the epilogue stages each warp's 32 x 64-channel bf16 block in (swizzled) shared memory and writes it with one
 // TMA store (full 128-byte lines, asynchronous); the ReLU-mask block of a dgrad is fetched the same way round (coalesced
 // 512-byte warp loads into the staging block).  Without it each lane stores its own 64 bytes at a 128-byte stride.
-template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, bool POOL = false>
+template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, int ROWS = 0>
 __global__ void __launch_bounds__(256, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask_src, const uint32_t* __restrict__ mask_bits,
                uint32_t* __restrict__ mask_out, __nv_bfloat16* __restrict__ out_bf, float* __restrict__ out_f32, int relu) {
+  constexpr bool POOL = ROWS == 1;
+  static_assert(ROWS == 0 || (N_OUT == 64 && T == 2 && CB == 1 && WRES), "row tiles: 64 -> 64 channels, two row tiles, resident weights");
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   const int abuf_bytes = g.abuf_rows * 128;                       // one 64-channel block of one buffer
@@ -105,7 +114,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       auto load_item = [&](int it) {
         const int b = it & 1;
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int q0 = POOL ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 : item * T * 128;
+        const int q0 = ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 : item * T * 128;
         mbar_wait(&a_empty[b], ((it >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&a_full[b], (uint32_t)(CB * abuf_bytes));
         for (int cb = 0; cb < CB; ++cb) {
@@ -136,8 +145,46 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
     constexpr uint32_t idesc = make_idesc_bf16(128, N_OUT, 0, 0);
     const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
     if (WRES) { mbar_wait(&w_full[0], 0); tc_fence_after(); }
-    const uint32_t tile_step = POOL ? (uint32_t)g.Wp * 8 : 1024u;   // 16-byte units between the tiles of an item
     uint32_t wcount = 0;
+    if constexpr (ROWS != 0) {
+      constexpr uint32_t idesc64 = make_idesc_bf16(128, 64, 0, 0), idesc128 = make_idesc_bf16(128, 128, 0, 0);
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&a_full[b], ph);
+        mbar_wait(&t_empty[b], ph ^ 1);
+        tc_fence_after();
+        const uint32_t a_row0 = a_addr0 + (uint32_t)b * abuf_bytes + (uint32_t)g.hh * 128;   // first interior position of row 2y
+        const uint32_t d0 = tmem_base + (uint32_t)(b * T * N_OUT);                             // O[2y] | O[2y+1]
+#pragma unroll 1
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t wk = w_addr0 + (uint32_t)(kx * 3) * 64 * 128;      // blocks ky = +1, 0, -1 of this kx
+          // input row (relative) -> weight blocks / accumulators:
+          //   r =  0: [W(0) | W(-1)] -> O0, O1     r = 1: [W(+1) | W(0)] -> O0, O1     r = -1: W(-1) -> O0     r = 2: W(+1) -> O1
+          const uint32_t a0 = desc_lo(a_row0 + (uint32_t)((kx - 1) * 128), 16);
+          const uint32_t a1 = desc_lo(a_row0 + (uint32_t)((g.Wp + kx - 1) * 128), 16);
+          const uint32_t am = desc_lo(a_row0 + (uint32_t)((-g.Wp + kx - 1) * 128), 16);
+          const uint32_t a2 = desc_lo(a_row0 + (uint32_t)((2 * g.Wp + kx - 1) * 128), 16);
+          const uint32_t w_p1 = desc_lo(wk, 16), w_0 = desc_lo(wk + 64 * 128, 16), w_m1 = desc_lo(wk + 2 * 64 * 128, 16);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0, desc_from_lo(a0 + k * 2), desc_from_lo(w_0 + k * 2), idesc128, (kx > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0, desc_from_lo(a1 + k * 2), desc_from_lo(w_p1 + k * 2), idesc128, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0, desc_from_lo(am + k * 2), desc_from_lo(w_m1 + k * 2), idesc64, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d0 + 64, desc_from_lo(a2 + k * 2), desc_from_lo(w_p1 + k * 2), idesc64, 1u);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          umma_commit(&t_full[b]);
+          umma_commit(&a_empty[b]);
+        }
+        __syncwarp();
+      }
+    } else
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
       const uint32_t ph = (it >> 1) & 1;
@@ -166,7 +213,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
           for (int t = 0; t < T; ++t) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)     // +tile_step (16-byte units) per tile, +2 per 32-byte k-step
-              umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * tile_step + k * 2), desc_from_lo(w_lo + k * 2), idesc,
+              umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
                         (kb > 0 || k > 0) ? 1u : 0u);
           }
           if (!WRES) umma_commit(&w_empty[s]);
@@ -183,7 +230,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
     if constexpr (POOL) {
-      static_assert(!POOL || (N_OUT == 64 && T == 2 && CB == 1), "POOL variant: 64 -> 64 channels, two row tiles");
       const int ew = warp - 4;
       const int OH = g.H >> 1, OW = g.W >> 1;
       const int x = ew * 32 + lane;                 // column of this thread (W == 128 == tile rows)
@@ -248,7 +294,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
         tc_fence_after();
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-          const int q0w = (item * T + t) * 128 + ew * 32;       // first position of this warp's block
+          // first position of this warp's block (row tiles: interior of image row 2y + t)
+          const int q0w = ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1 + t) * g.Wp + 1 + ew * 32
+                               : (item * T + t) * 128 + ew * 32;
           const int q = q0w + lane;
           const int n = q / HpWp, rem = q - n * HpWp;
           const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
@@ -262,7 +310,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
           uint32_t mo[N_OUT / 32];
 #pragma unroll
           for (int hf = 0; hf < N_OUT / 64; ++hf) {
-            if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
+            // the staging block is still being read by the previous TMA store: wait as late as possible (right before the
+            // first shared-memory write) so the TMEM load and the arithmetic of this block overlap that read
+            if (mask_src && store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
             if (mask_src) {
               // 32 rows x 128 B of the mask stream, 4 rows (512 contiguous bytes) per warp instruction
 #pragma unroll
@@ -301,6 +351,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
                 for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
                 mo[c] = w;
               }
+              if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
 #pragma unroll
               for (int j4 = 0; j4 < 4; ++j4) {
                 const uint32_t addr = my_row + (uint32_t)(((c2 * 4 + j4) ^ sw) << 4);
