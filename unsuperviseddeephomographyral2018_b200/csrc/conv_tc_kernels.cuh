@@ -290,23 +290,38 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       for (int it = 0; it < my_items; ++it) {
         const int b = it & 1;
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        // first position of this warp's block in tile 0 and the distance to tile 1 (row tiles: interior of image row 2y + t)
+        const int q0w0 = ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 + ew * 32 : item * T * 128 + ew * 32;
+        const int qstep = ROWS ? g.Wp : 128;
+        // ReLU-backward mask of a dgrad as 1 bit / element (written by the forward of the layer below): one 8/16-byte load
+        // per position instead of a 128/256-byte bf16 row.  Both tiles' words are requested BEFORE waiting for the
+        // accumulators so the global-load latency hides behind the MMAs (the epilogue warps are the critical path of a dgrad).
+        uint32_t mbt[2][N_OUT / 32];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int qt = q0w0 + t * qstep + lane;
+          const bool ok = mask_bits && t < T && qt < g.Q;
+          if (N_OUT == 64) {
+            const uint2 m = ok ? __ldg(reinterpret_cast<const uint2*>(mask_bits + (size_t)qt * 2)) : make_uint2(0u, 0u);
+            mbt[t][0] = m.x; mbt[t][1] = m.y;
+          } else {
+            const uint4 m = ok ? __ldg(reinterpret_cast<const uint4*>(mask_bits + (size_t)qt * 4)) : make_uint4(0u, 0u, 0u, 0u);
+            mbt[t][0] = m.x; mbt[t][1] = m.y; mbt[t][N_OUT / 32 - 2] = m.z; mbt[t][N_OUT / 32 - 1] = m.w;
+          }
+        }
         mbar_wait(&t_full[b], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
-          // first position of this warp's block (row tiles: interior of image row 2y + t)
-          const int q0w = ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1 + t) * g.Wp + 1 + ew * 32
-                               : (item * T + t) * 128 + ew * 32;
+          const int q0w = q0w0 + t * qstep;
           const int q = q0w + lane;
           const int n = q / HpWp, rem = q - n * HpWp;
           const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
           const bool valid = q < g.Q && xp >= 1 && xp <= g.W && yp >= 1 && yp <= g.H;
           const size_t o_f32 = (((size_t)n * g.H + (yp - 1)) * g.W + (xp - 1)) * N_OUT;
-          // ReLU-backward mask of a dgrad as 1 bit / element (written by the forward of the layer below): one 8/16-byte
-          // load per position instead of a 128/256-byte bf16 row
           uint32_t mb[N_OUT / 32];
 #pragma unroll
-          for (int i = 0; i < N_OUT / 32; ++i) mb[i] = (mask_bits && q < g.Q) ? __ldg(mask_bits + (size_t)q * (N_OUT / 32) + i) : 0u;
+          for (int i = 0; i < N_OUT / 32; ++i) mb[i] = t ? mbt[1][i] : mbt[0][i];
           uint32_t mo[N_OUT / 32];
 #pragma unroll
           for (int hf = 0; hf < N_OUT / 64; ++hf) {
@@ -408,7 +423,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       tc_fence_after();
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-        const int q = (item * T + t) * 128 + ew * 32 + lane;
+        const int q = (ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1 + t) * g.Wp + 1 : (item * T + t) * 128) + ew * 32 + lane;
         const int n = q / HpWp, rem = q - n * HpWp;
         const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
         const bool valid = q < g.Q && xp >= 1 && xp <= g.W && yp >= 1 && yp <= g.H;
