@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/udh.h"
 
@@ -65,6 +66,30 @@ inline int check_launch(const char* what) {
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch (PDL) for the back-to-back kernels of the bf16 step ---------------------------------
+// A kernel launched through launch_chain() may be scheduled while its predecessor in the stream is still draining: its CTAs
+// take over SMs as the predecessor's CTAs exit and run their prologue (barrier init, TMEM allocation, tensor-map prefetch)
+// early.  Every such kernel calls pdl_wait() before its first global-memory access (it returns once the predecessor grid
+// has completed and its writes are visible) and pdl_trigger() right after, so completion is transitive along the chain.
+// UDH_PDL=0 in the environment falls back to plain launches (griddepcontrol.wait is then a no-op).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("UDH_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);     // errors surface through check_launch()
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

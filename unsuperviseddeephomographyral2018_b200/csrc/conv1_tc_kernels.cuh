@@ -97,6 +97,8 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // predecessor grid complete (the prologue above touched only parameters, written long before)
+  pdl_trigger();
   const int my_tiles = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int segs = g.W / 128;
 
@@ -219,6 +221,8 @@ conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // predecessor grid complete (the prologue above touched only parameters, written long before)
+  pdl_trigger();
   const int my_tiles = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int segs = g.W / 128;
 

@@ -87,6 +87,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // all seven tensor-core layers in one launch (both directions): blockIdx.y = layer-1, blockIdx.z = direction
 struct PackTable { const float* w[7]; __nv_bfloat16* fwd[7]; __nv_bfloat16* dgr[7]; int cin[7], cout[7]; int rowtile_fwd[7], rowtile_dgr[7]; };
 __global__ void pack_all_weights_kernel(PackTable t, int do_fwd, int do_dgrad) {
+  pdl_wait(); pdl_trigger();
   const int L = blockIdx.y, dgrad = blockIdx.z;
   if ((dgrad && !do_dgrad) || (!dgrad && !do_fwd)) return;
   const int Cin = t.cin[L], Cout = t.cout[L];
@@ -106,6 +107,7 @@ __global__ void pack_all_weights_kernel(PackTable t, int do_fwd, int do_dgrad) {
 
 // fp32 [B,H,W,C] -> bf16 padded [B,H+2,W+2,C] interior (borders untouched = zero)
 __global__ void pad_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W, int C) {
+  pdl_wait(); pdl_trigger();
   const int C4 = C >> 2;
   const size_t total = (size_t)B * H * W * C4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -161,6 +163,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // gradients from these codes and never re-reads the pre-pool activations.
 __global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, uint32_t* __restrict__ codes,
                                      int B, int H, int W, int C) {
+  pdl_wait(); pdl_trigger();
   const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
   const size_t total = (size_t)B * OH * OW * C8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -194,6 +197,7 @@ __global__ void pool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_
 // gradient routing of the above + ReLU mask of the producer, from the forward's routing codes
 __global__ void pool_bwd_bf16_kernel(const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ gout,
                                      __nv_bfloat16* __restrict__ gin, int B, int H, int W, int C) {
+  pdl_wait(); pdl_trigger();
   const int C8 = C >> 3, OH = H >> 1, OW = W >> 1;
   const size_t total = (size_t)B * OH * OW * C8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -228,7 +232,7 @@ int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const 
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
-  kern<<<grid, 256, smem, st>>>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
+  launch_chain(kern, dim3(grid), dim3(256), smem, st, tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
   return check_launch("tc_conv_kernel");
 }
 
@@ -334,7 +338,7 @@ int pack_weights(const float* w, __nv_bfloat16* dst, int cin, int cout, int dgra
 }
 int pad_cast(const float* src, __nv_bfloat16* dst, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * H * W * (C / 4);
-  pad_cast_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(src, dst, B, H, W, C);
+  launch_chain(pad_cast_kernel, dim3(grid1d((total + 255) / 256, 148 * 32)), dim3(256), 0, st, src, dst, B, H, W, C);
   return check_launch("pad_cast");
 }
 int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C, cudaStream_t st) {
@@ -344,12 +348,12 @@ int unpad_cast(const __nv_bfloat16* src, float* dst, int B, int H, int W, int C,
 }
 int pool_fwd_bf16(const __nv_bfloat16* in, __nv_bfloat16* out, uint32_t* codes, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  pool_fwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(in, out, codes, B, H, W, C);
+  launch_chain(pool_fwd_bf16_kernel, dim3(grid1d((total + 255) / 256, 148 * 32)), dim3(256), 0, st, in, out, codes, B, H, W, C);
   return check_launch("pool_fwd_bf16");
 }
 int pool_bwd_bf16(const uint32_t* codes, const __nv_bfloat16* gout, __nv_bfloat16* gin, int B, int H, int W, int C, cudaStream_t st) {
   const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
-  pool_bwd_bf16_kernel<<<grid1d((total + 255) / 256, 148 * 32), 256, 0, st>>>(codes, gout, gin, B, H, W, C);
+  launch_chain(pool_bwd_bf16_kernel, dim3(grid1d((total + 255) / 256, 148 * 32)), dim3(256), 0, st, codes, gout, gin, B, H, W, C);
   return check_launch("pool_bwd_bf16");
 }
 
@@ -386,7 +390,7 @@ int launch_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, f
   UDH_REQUIRE(smem <= 232448, "tc wgrad: %zu bytes of shared memory exceed the 227 KiB limit", smem);
   auto kern = tc::tc_wgrad_kernel<N_OUT, CBX, T>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<g.slice_cta[g.num_slices], 256, smem, st>>>(tmX128, tmXhh, tmG, g, dW, db);
+  launch_chain(kern, dim3(g.slice_cta[g.num_slices]), dim3(256), smem, st, tmX128, tmXhh, tmG, g, dW, db);
   return check_launch("tc_wgrad_kernel");
 }
 
@@ -412,7 +416,7 @@ int launch_wgrad64(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW,
   auto kern = tc::tc_wgrad64_kernel<T>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
-  kern<<<g.num_items < sms ? g.num_items : sms, 256, smem, st>>>(tmX128, tmXhh, tmG136, g, dW, db);
+  launch_chain(kern, dim3(g.num_items < sms ? g.num_items : sms), dim3(256), smem, st, tmX128, tmXhh, tmG136, g, dW, db);
   return check_launch("tc_wgrad64_kernel");
 }
 
@@ -427,6 +431,7 @@ int tc_wgrad(const __nv_bfloat16* x, const __nv_bfloat16* gsrc, float* dW, float
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+  pdl_wait(); pdl_trigger();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
     __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
@@ -435,7 +440,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
-  cast_bf16_kernel<<<grid1d((n / 4 + 255) / 256, 148 * 16), 256, 0, st>>>(src, dst, n / 4);
+  launch_chain(cast_bf16_kernel, dim3(grid1d((n / 4 + 255) / 256, 148 * 16)), dim3(256), 0, st, src, dst, n / 4);
   return check_launch("cast_bf16");
 }
 
@@ -467,7 +472,7 @@ int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, cons
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
-  kern<<<tiles < sms ? tiles : sms, 256, smem, st>>>(tmA, tmB, tmC, g, C);
+  launch_chain(kern, dim3(tiles < sms ? tiles : sms), dim3(256), smem, st, tmA, tmB, tmC, g, C);
   return check_launch("tc_gemm_kernel");
 }
 
@@ -485,7 +490,7 @@ int conv1_tc_fwd(const float* I1, const float* I2, const float* w, const float* 
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int want = tc::kConv1CtasPerSm * persistent_ctas();
   const int grid = g.tiles < want ? g.tiles : want;
-  tc::conv1_tc_fwd_kernel<<<grid, 160, smem, st>>>(tmOut, g, I1, I2, w, bias, mask_out);
+  launch_chain(tc::conv1_tc_fwd_kernel, dim3(grid), dim3(160), smem, st, tmOut, g, I1, I2, w, bias, mask_out);
   return check_launch("conv1_tc_fwd_kernel");
 }
 
@@ -502,7 +507,7 @@ int conv1_tc_wgrad(const float* I1, const float* I2, const __nv_bfloat16* G_pad,
   UDH_CUDA(cudaFuncSetAttribute(tc::conv1_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int want = tc::kConv1CtasPerSm * persistent_ctas();
   const int grid = g.tiles < want ? g.tiles : want;
-  tc::conv1_tc_wgrad_kernel<<<grid, 160, smem, st>>>(tmG, g, I1, I2, dW, db);
+  launch_chain(tc::conv1_tc_wgrad_kernel, dim3(grid), dim3(160), smem, st, tmG, g, I1, I2, dW, db);
   return check_launch("conv1_tc_wgrad_kernel");
 }
 
@@ -540,7 +545,7 @@ int tc_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
       t.rowtile_fwd[i - 1] = (i == 1 && P == 128) ? 1 : 0;          // conv1_2 forward runs on row tiles (fused with pool1)
       t.rowtile_dgr[i - 1] = (i == 1 && P == 128) ? 1 : 0;          // ... and so does its dgrad
     }
-    pack_all_weights_kernel<<<dim3(72, 7, 2), 256, 0, st>>>(t, 1, 1);
+    launch_chain(pack_all_weights_kernel, dim3(72, 7, 2), dim3(256), 0, st, t, 1, 1);
     TRY(check_launch("pack_all_weights"));
   }
   {

@@ -102,6 +102,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int my_items = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x + i*gridDim.x
+  pdl_wait();                  // predecessor grid complete: global memory may be touched from here on
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================

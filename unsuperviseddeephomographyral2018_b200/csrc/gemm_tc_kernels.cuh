@@ -53,6 +53,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = g.m_tiles * g.n_tiles * g.k_splits;
+  pdl_wait();                  // predecessor grid complete: global memory may be touched from here on
+  pdl_trigger();
   const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   auto decode = [&](int tile, int& mt, int& nt, int& ks) {

@@ -75,6 +75,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // predecessor grid complete: global memory may be touched from here on
+  pdl_trigger();
   const int my_items = (g.num_items - bx + gxs - 1) / gxs;
 
   if (warp == 0) {
@@ -241,6 +243,8 @@ tc_wgrad64_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // predecessor grid complete: global memory may be touched from here on
+  pdl_trigger();
   const int my_items = (g.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0) {
