@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     const float* __restrict__ Bm, int64_t b_rs, int64_t b_cs,
                                                     float* __restrict__ C, int64_t ldc, int M, int N, int K, int k_chunk,
                                                     int atomic) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ __align__(16) float As[16][68];
   __shared__ __align__(16) float Bs[16][68];
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
@@ -327,6 +328,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 __global__ void bias_act_dropout_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ act,
                                         float* __restrict__ drop, uint8_t* __restrict__ mask, int rows, int cols, int relu,
                                         int gen_mask, uint64_t seed, uint64_t salt) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   const size_t total = (size_t)rows * cols;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     float v = x[i] + (bias ? __ldg(bias + (i % cols)) : 0.f);
@@ -346,6 +348,7 @@ __global__ void bias_act_dropout_kernel(const float* __restrict__ x, const float
 
 __global__ void drop_relu_bwd_kernel(float* __restrict__ g, const uint8_t* __restrict__ mask, const float* __restrict__ act,
                                      size_t n) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = g[i];
     if (mask) v = mask[i] ? v * 2.0f : 0.f;
@@ -354,6 +357,7 @@ __global__ void drop_relu_bwd_kernel(float* __restrict__ g, const uint8_t* __res
 }
 
 __global__ void colsum_kernel(const float* __restrict__ g, float* __restrict__ db, int rows, int cols) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -424,16 +428,16 @@ int sgemm_simt(const float* A, int64_t a_rs, int64_t a_cs, const float* Bm, int6
   int k_chunk = ((K + split_k - 1) / split_k + 15) / 16 * 16;
   split_k = (K + k_chunk - 1) / k_chunk;
   dim3 grid((N + 63) / 64, (M + 63) / 64, split_k);
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, C, ldc, M, N, K, k_chunk,
-                                     (split_k > 1 || accumulate) ? 1 : 0);
+  launch_chain(sgemm_kernel, grid, dim3(256), 0, st, A, a_rs, a_cs, Bm, b_rs, b_cs, C, ldc, M, N, K, k_chunk,
+               (split_k > 1 || accumulate) ? 1 : 0);
   return check_launch("sgemm_simt");
 }
 
 int bias_act_dropout(const float* x, const float* bias, float* act, float* drop, uint8_t* mask, int rows, int cols,
                      int relu, int gen_mask, uint64_t seed, uint64_t salt, cudaStream_t st) {
   const size_t total = (size_t)rows * cols;
-  bias_act_dropout_kernel<<<grid1d((total + 255) / 256, 148 * 16), 256, 0, st>>>(
-      x, bias, act, drop, mask, rows, cols, relu, gen_mask, seed, salt);
+  launch_chain(bias_act_dropout_kernel, dim3(grid1d((total + 255) / 256, 148 * 16)), dim3(256), 0, st,
+               x, bias, act, drop, mask, rows, cols, relu, gen_mask, seed, salt);
   return check_launch("bias_act_dropout");
 }
 
@@ -442,13 +446,13 @@ int dropout_fwd(const float* x, float* drop, uint8_t* mask, size_t n, uint64_t s
 }
 
 int drop_relu_bwd(float* g, const uint8_t* mask, const float* act, size_t n, cudaStream_t st) {
-  drop_relu_bwd_kernel<<<grid1d((n + 255) / 256, 148 * 16), 256, 0, st>>>(g, mask, act, n);
+  launch_chain(drop_relu_bwd_kernel, dim3(grid1d((n + 255) / 256, 148 * 16)), dim3(256), 0, st, g, mask, act, n);
   return check_launch("drop_relu_bwd");
 }
 
 int colsum_accum(const float* g, float* db, int rows, int cols, cudaStream_t st) {
   dim3 grid((cols + 127) / 128, min(rows, 16));
-  colsum_kernel<<<grid, 128, 0, st>>>(g, db, rows, cols);
+  launch_chain(colsum_kernel, grid, dim3(128), 0, st, g, db, rows, cols);
   return check_launch("colsum_accum");
 }
 

@@ -59,6 +59,7 @@ __device__ __forceinline__ void build_row(const float* __restrict__ p1, const fl
 
 __global__ void __launch_bounds__(128) dlt_fwd_kernel(const float* __restrict__ pts1, const float* __restrict__ h4p,
                                                       float* __restrict__ H, int B) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;                                        // warp-uniform
@@ -128,7 +129,7 @@ extern "C" int udh_dlt_fwd(const float* pts1, const float* h4p, float* H, int B,
   UDH_REQUIRE(pts1 && h4p && H && B >= 0, "udh_dlt_fwd: null pointer or negative batch");
   if (B == 0) return UDH_OK;
   udh::ProfScope ps(udh::PROF_DLT, udh::as_stream(stream));
-  udh::dlt_fwd_kernel<<<(B + 3) / 4, 128, 0, udh::as_stream(stream)>>>(pts1, h4p, H, B);
+  udh::launch_chain(udh::dlt_fwd_kernel, dim3((B + 3) / 4), dim3(128), 0, udh::as_stream(stream), pts1, h4p, H, B);
   return udh::check_launch("udh_dlt_fwd");
 }
 

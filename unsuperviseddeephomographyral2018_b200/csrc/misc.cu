@@ -57,6 +57,7 @@ void prof_end(int tag, cudaStream_t st) {
 __global__ void __launch_bounds__(256) h4p_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int B,
                                                        float* __restrict__ metrics, float* __restrict__ per_sample,
                                                        float* __restrict__ dpred) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ double red[4 * 32];
   __shared__ float s_hloss;
   double acc[4] = {0, 0, 0, 0};   // sum sq, sum bounded, num fail, sum corner distance
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
                                                    float4* __restrict__ v, size_t n4, float alpha, float b1, float b2,
                                                    float eps, float gs, int zero_grad, uint2* __restrict__ mirror,
                                                    size_t mb4, size_t me4, int keep_grad) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   const float c1 = 1.0f - b1, c2 = 1.0f - b2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 pv = p[i], gv = g[i], mv = m[i], vv = v[i];
@@ -171,7 +173,7 @@ extern "C" int udh_h4p_loss(const float* pred, const float* gt, int B, float* me
                             void* stream) {
   UDH_REQUIRE(pred && gt && metrics && B >= 1, "udh_h4p_loss: bad arguments");
   udh::ProfScope ps(udh::PROF_H4P_LOSS, udh::as_stream(stream));
-  udh::h4p_loss_kernel<<<1, 256, 0, udh::as_stream(stream)>>>(pred, gt, B, metrics, per_sample, dpred);
+  udh::launch_chain(udh::h4p_loss_kernel, dim3(1), dim3(256), 0, udh::as_stream(stream), pred, gt, B, metrics, per_sample, dpred);
   return udh::check_launch("udh_h4p_loss");
 }
 
@@ -193,7 +195,7 @@ extern "C" int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size
   const size_t n4 = n / 4;
   const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   udh::ProfScope ps(udh::PROF_ADAM, udh::as_stream(stream));
-  udh::adam_kernel<<<blocks, 256, 0, udh::as_stream(stream)>>>((float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
+  udh::launch_chain(udh::adam_kernel, dim3(blocks), dim3(256), 0, udh::as_stream(stream), (float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
                                                               beta1, beta2, eps, grad_scale, zero_grad, (uint2*)mirror,
                                                               mirror_begin / 4, (mirror_begin + mirror_count) / 4, mirror_keep_grad);
   return udh::check_launch("udh_adam_step");

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
                                                             const int32_t* __restrict__ patch_indices, int64_t idx_stride,
                                                             int pw, int ph, float* __restrict__ pred,
                                                             double* __restrict__ sums) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ double red[UDH_NSUMS * 32];
   const int b = blockIdx.y;
   const int tiles_x = (pw + 127) >> 7;
@@ -319,6 +320,7 @@ __global__ void conj_bwd_kernel(const float* __restrict__ dHn, float* __restrict
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ X, const float* __restrict__ Y, int pw, int ph,
                                                    double* __restrict__ sums) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ double red[32];
   const int b = blockIdx.y;
   const int ow = pw - 2, oh = ph - 2;
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
 }
 
 __global__ void photo_finalize_kernel(const double* __restrict__ sums, double n, double n_ssim, float* __restrict__ out) {
+  pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   out[UDH_L_REC] = (float)sqrt(sums[UDH_SUM_SQ] / n);
   out[UDH_L_SSIM] = n_ssim > 0 ? (float)(sums[UDH_SUM_SSIM] / n_ssim) : 0.f;
@@ -444,9 +447,9 @@ extern "C" int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, co
   dim3 grid(((pw + 127) / 128) * ((ph + 31) / 32), B);
   ProfScope ps(PROF_WARP_FWD, as_stream(stream));
   if (C == 3)
-    warp_loss_fwd_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+    launch_chain(warp_loss_fwd_kernel<3>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
   else
-    warp_loss_fwd_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+    launch_chain(warp_loss_fwd_kernel<1>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
   return check_launch("udh_warp_loss_fwd");
 }
 
@@ -493,7 +496,7 @@ extern "C" int udh_ssim_fwd(const float* pred, const float* I2, int pw, int ph, 
   const int n = (pw - 2) * (ph - 2);
   dim3 grid(min((n + 255) / 256, 64), B);
   ProfScope ps(PROF_SSIM, as_stream(stream));
-  ssim_kernel<<<grid, 256, 0, as_stream(stream)>>>(pred, I2, pw, ph, sums);
+  launch_chain(ssim_kernel, grid, dim3(256), 0, as_stream(stream), pred, I2, pw, ph, sums);
   return check_launch("udh_ssim_fwd");
 }
 
@@ -510,7 +513,7 @@ extern "C" int udh_ssim_bwd(const float* pred, const float* I2, int pw, int ph, 
 
 extern "C" int udh_photo_losses_finalize(const double* sums, double n, double n_ssim, float* losses, void* stream) {
   UDH_REQUIRE(sums && losses && n > 0, "udh_photo_losses_finalize: bad arguments");
-  photo_finalize_kernel<<<1, 32, 0, as_stream(stream)>>>(sums, n, n_ssim, losses);
+  launch_chain(photo_finalize_kernel, dim3(1), dim3(32), 0, as_stream(stream), sums, n, n_ssim, losses);
   return check_launch("udh_photo_losses_finalize");
 }
 
