@@ -232,7 +232,7 @@ int launch_conv_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const 
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
-  launch_chain(kern, dim3(grid), dim3(256), smem, st, tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
+  launch_chain(kern, dim3(grid), dim3(tc::conv_threads<TMA_EPI>()), smem, st, tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu);
   return check_launch("tc_conv_kernel");
 }
 
@@ -261,7 +261,7 @@ int launch_conv(const __nv_bfloat16* x, const __nv_bfloat16* wpk, const float* b
   TRY(tc::make_tmap_bf16(&tmOut, out_bf, 2, dimsO, strO, boxO));
   // TMA-store epilogue when its 16 KiB staging block still fits next to the operand buffers
   const size_t smem_tma = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows, true);
-  if (out_bf && smem_tma <= 232448)
+  if (out_bf && !mask_src && smem_tma <= 232448)
     return launch_conv_impl<N_OUT, CB, T, WRES, true>(tmA128, tmAhh, tmW, tmOut, g, bias, mask_src, mask_bits, mask_out, out_bf, out_f32, relu,
                                                       smem_tma, st);
   const size_t smem = tc::ConvSmem<N_OUT, CB, T, WRES>::bytes(g.abuf_rows, false);

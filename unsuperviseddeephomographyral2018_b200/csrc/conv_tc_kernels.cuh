@@ -59,8 +59,11 @@ struct ConvSmem {
 // TMA_EPI: the epilogue stages each warp's 32 x 64-channel bf16 block in (swizzled) shared memory and writes it with one
 // TMA store (full 128-byte lines, asynchronous); the ReLU-mask block of a dgrad is fetched the same way round (coalesced
 // 512-byte warp loads into the staging block).  Without it each lane stores its own 64 bytes at a 128-byte stride.
+// threads per CTA: 4 control warps (TMA, MMA, TMEM alloc, idle) + 4 epilogue warps, or 8 with the TMA-store epilogue
+template <bool TMA_EPI> __host__ __device__ constexpr int conv_threads() { return TMA_EPI ? 384 : 256; }
+
 template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, int ROWS = 0>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(conv_threads<TMA_EPI>(), 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ mask_src, const uint32_t* __restrict__ mask_bits,
@@ -90,7 +93,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1);
-      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128);
+      mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], conv_threads<TMA_EPI>() - 128);
     }
     for (int i = 0; i < kNumWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     fence_barrier_init();
@@ -283,21 +286,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
         mbar_arrive(&t_empty[b]);
       }
     } else if (TMA_EPI) {
-      const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
+      // TWO epilogue warps per TMEM lane quarter (warps 4-7 and 8-11): the epilogue, not the MMA stream, paces the layers
+      // that store full-resolution bf16 outputs, so warp group eg handles the 32-column chunk eg of every 64-channel half.
+      // Both warps of a quarter fill their halves of the quarter's 32 x 128 B staging block, meet at a 64-thread named
+      // barrier, and one lane issues the TMA store of the block.
+      const int eg = (warp - 4) >> 2;               // column chunk within a 64-channel half
+      const int ew = (warp - 4) & 3;                // TMEM lane quarter == warp index % 4
       const int HpWp = g.Hp * g.Wp;
-      uint8_t* stg = sEpi + ew * 4096;              // this warp's 32 x 128 B staging block (1024-byte aligned)
+      uint8_t* stg = sEpi + ew * 4096;              // the quarter's 32 x 128 B staging block (1024-byte aligned)
       const uint32_t my_row = smem_u32(stg) + lane * 128;
       const int sw = lane & 7;                      // 128-byte swizzle phase of this lane's row
+      const bool issuer = eg == 0 && lane == 0;     // the thread that owns the quarter's TMA-store bulk groups
+      auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + ew) : "memory"); };
       bool store_pending = false;
       for (int it = 0; it < my_items; ++it) {
         const int b = it & 1;
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        // first position of this warp's block in tile 0 and the distance to tile 1 (row tiles: interior of image row 2y + t)
+        // first position of this quarter's block in tile 0 and the distance to tile 1 (row tiles: interior of image row 2y + t)
         const int q0w0 = ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 + ew * 32 : item * T * 128 + ew * 32;
         const int qstep = ROWS ? g.Wp : 128;
         // ReLU-backward mask of a dgrad as 1 bit / element (written by the forward of the layer below): one 8/16-byte load
         // per position instead of a 128/256-byte bf16 row.  Both tiles' words are requested BEFORE waiting for the
-        // accumulators so the global-load latency hides behind the MMAs (the epilogue warps are the critical path of a dgrad).
+        // accumulators so the global-load latency hides behind the MMAs.
         uint32_t mbt[2][N_OUT / 32];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -321,99 +331,71 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
           const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
           const bool valid = q < g.Q && xp >= 1 && xp <= g.W && yp >= 1 && yp <= g.H;
           const size_t o_f32 = (((size_t)n * g.H + (yp - 1)) * g.W + (xp - 1)) * N_OUT;
-          uint32_t mb[N_OUT / 32];
-#pragma unroll
-          for (int i = 0; i < N_OUT / 32; ++i) mb[i] = t ? mbt[1][i] : mbt[0][i];
-          uint32_t mo[N_OUT / 32];
+          uint32_t mo[N_OUT / 64];                  // own chunk of each 64-channel half
 #pragma unroll
           for (int hf = 0; hf < N_OUT / 64; ++hf) {
-            // the staging block is still being read by the previous TMA store: wait as late as possible (right before the
-            // first shared-memory write) so the TMEM load and the arithmetic of this block overlap that read
-            if (mask_src && store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
-            if (mask_src) {
-              // 32 rows x 128 B of the mask stream, 4 rows (512 contiguous bytes) per warp instruction
+            const int c = hf * 2 + eg;
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
+            if (bias) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int row = i * 4 + (lane >> 3), ch = lane & 7;
-                uint4 m = make_uint4(0, 0, 0, 0);
-                if (q0w + row < g.Q) m = __ldg(reinterpret_cast<const uint4*>(mask_src + (size_t)(q0w + row) * N_OUT + hf * 64) + ch);
-                *reinterpret_cast<uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = m;
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
+                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
               }
-              __syncwarp();
             }
+            if (relu) {
 #pragma unroll
-            for (int c2 = 0; c2 < 2; ++c2) {
-              const int c = hf * 2 + c2;
-              float v[32];
-              tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
-              if (bias) {
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (mask_bits) {
+              const uint32_t w = t ? mbt[1][c] : mbt[0][c];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + j));
-                  v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-                }
+              for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
+            }
+            mo[hf] = 0u;
+            if (mask_out) {
+              uint32_t w = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
+              mo[hf] = w;
+            }
+            // the staging block is still being read by the previous TMA store: wait as late as possible (right before the
+            // first shared-memory write) so the TMEM load and the arithmetic above overlap that read
+            if (store_pending) { if (issuer) bulk_wait_read0(); pair_sync(); store_pending = false; }
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t addr = my_row + (uint32_t)(((eg * 4 + j4) ^ sw) << 4);
+              uint4 pk = make_uint4(0, 0, 0, 0);                               // border / out-of-range positions store zeros
+              if (valid) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j4 * 8 + 0], v[j4 * 8 + 1]);
+                __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j4 * 8 + 2], v[j4 * 8 + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j4 * 8 + 4], v[j4 * 8 + 5]);
+                __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j4 * 8 + 6], v[j4 * 8 + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
               }
-              if (relu) {
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+            }
+            if (out_f32 && valid) {
+              float4* fp = reinterpret_cast<float4*>(out_f32 + o_f32 + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (mask_bits) {
-                const uint32_t w = mb[c];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = ((w >> j) & 1u) ? v[j] : 0.f;
-              }
-              if (mask_out) {
-                uint32_t w = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f ? 1u : 0u) << j;
-                mo[c] = w;
-              }
-              if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
-#pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const uint32_t addr = my_row + (uint32_t)(((c2 * 4 + j4) ^ sw) << 4);
-                if (mask_src) {
-                  uint4 m;
-                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w) : "r"(addr));
-                  const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-                  for (int h = 0; h < 4; ++h) {
-                    const uint32_t lo = mw[h] & 0xFFFFu, hi = mw[h] >> 16;     // bf16 > 0 <=> non-zero magnitude, sign clear
-                    if (!(lo != 0 && !(lo & 0x8000u))) v[j4 * 8 + h * 2] = 0.f;
-                    if (!(hi != 0 && !(hi & 0x8000u))) v[j4 * 8 + h * 2 + 1] = 0.f;
-                  }
-                }
-                uint4 pk = make_uint4(0, 0, 0, 0);                             // border / out-of-range positions store zeros
-                if (valid) {
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j4 * 8 + 0], v[j4 * 8 + 1]);
-                  __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j4 * 8 + 4], v[j4 * 8 + 5]);
-                  __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                }
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-              }
-              if (out_f32 && valid) {
-                float4* fp = reinterpret_cast<float4*>(out_f32 + o_f32 + c * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) fp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              }
+              for (int j = 0; j < 8; ++j) fp[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             fence_proxy_async();                    // generic-proxy smem writes -> visible to the TMA engine
-            __syncwarp();
-            if (lane == 0 && q0w < g.Q) { tma_store_2d(&tmOut, stg, hf * 64, q0w); bulk_commit(); }
+            pair_sync();                            // both 64-byte halves of every row are in place
+            if (issuer && q0w < g.Q) { tma_store_2d(&tmOut, stg, hf * 64, q0w); bulk_commit(); }
             store_pending = true;
           }
           if (mask_out && q < g.Q) {
 #pragma unroll
-            for (int i = 0; i < N_OUT / 32; ++i) mask_out[(size_t)q * (N_OUT / 32) + i] = valid ? mo[i] : 0u;
+            for (int hf = 0; hf < N_OUT / 64; ++hf) mask_out[(size_t)q * (N_OUT / 32) + hf * 2 + eg] = valid ? mo[hf] : 0u;
           }
         }
         tc_fence_before();
         mbar_arrive(&t_empty[b]);
       }
-      if (lane == 0) bulk_wait0();
+      if (issuer) bulk_wait0();
       __syncwarp();
     } else {
     const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
