@@ -10,14 +10,14 @@ MACS = {"conv1_2": 603.98e6, "conv2_1": 150.99e6, "conv2_2": 150.99e6, "conv3_1"
 
 
 NOTES_CONV = [
-    "Reading.  conv1_2.fwd runs on ROW TILES fused with pool1 (`tc_conv_kernel<64,1,2,1,0,1>`): DRAM read 277 MB = the bf16 input stream once, DRAM write 65 MB = the pooled",
+    "Reading.  conv1_2.fwd runs on ROW TILES fused with pool1 (`tc_conv_kernel<64,1,2,1,0,1>`): DRAM read 277 MB = the bf16 input stream once, DRAM write 64 MB = the pooled",
     "stream + routing codes (the full-resolution activation is never written), tensor pipe active 67 % — its MMAs are organised by input row so that half of them are",
     "N = 128 (two adjacent weight blocks -> two adjacent accumulators).  An (M128,N64,K16) MMA cannot go below ~50 clk (A-operand fetch, tools/tc_probe2.py,",
     "profiles/r1_tc_probe2.log: 49.8 clk with cta_group::1 AND cta_group::2), i.e. plain N = 64 layers cap at 64 % of the tensor peak; the stream-tiled 64-channel launches",
-    "(conv2_x) sit at 42-49 % active = 66-76 % of that cap with 15 items per CTA.  conv1_2.dgrad (`<64,1,2,1,1,2>`, row tiles, TMA-store epilogue + 1-bit ReLU mask) is",
-    "EPILOGUE-bound: PC sampling puts the four epilogue warps at 5 % waiting for accumulators, the rest in their own work (mask words, TMEM loads, bf16 pack, staging,",
-    "TMA store), tensor pipe 47 %.  The <128,2,2,0,*> launches are the 32x32 / 16x16 layers: few tiles (162 items for 148 SMs at 16x16) and weights streamed from L2",
-    "(288 KB per item), hence the lower utilisation; they are 18 % of the family's time.",
+    "(conv2_x) sit at 46-49 % active = 72-76 % of that cap with 15 items per CTA.  conv1_2.dgrad (`<64,1,2,1,1,2>`, row tiles, TMA-store epilogue + 1-bit ReLU mask) is",
+    "EPILOGUE-paced (PC sampling of the previous build: the epilogue warps spent 5 % of their time waiting for accumulators); with two epilogue warps per TMEM lane quarter",
+    "(384 threads, 111-124 registers) it went from 169 us / 47 % to 152 us / 53 % tensor-pipe active.  The <128,2,2,0,*> launches are the 32x32 / 16x16 layers: few tiles",
+    "(162 items for 148 SMs at 16x16) and weights streamed from L2 (288 KB per item), hence the lower utilisation; they are 17 % of the family's time.",
 ]
 NOTES_WG = [
     "Reading.  tc_wgrad64_kernel (64 -> 64 layers) issues TWO (M128,N192,K16) MMAs per 16 positions (A = two row shifts of X, B = three row shifts of G): conv1_2.wgrad",
