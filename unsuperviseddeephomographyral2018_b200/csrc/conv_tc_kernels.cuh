@@ -59,8 +59,9 @@ struct ConvSmem {
 // TMA_EPI: the epilogue stages each warp's 32 x 64-channel bf16 block in (swizzled) shared memory and writes it with one
 // TMA store (full 128-byte lines, asynchronous); the ReLU-mask block of a dgrad is fetched the same way round (coalesced
 // 512-byte warp loads into the staging block).  Without it each lane stores its own 64 bytes at a 128-byte stride.
-// threads per CTA: 4 control warps (TMA, MMA, TMEM alloc, idle) + 4 epilogue warps, or 8 with the TMA-store epilogue
-template <bool TMA_EPI> __host__ __device__ constexpr int conv_threads() { return TMA_EPI ? 384 : 256; }
+// threads per CTA: 4 control warps (TMA, MMA, TMEM alloc, idle) + 8 epilogue warps (two per TMEM lane quarter, each owning
+// every second 32-column chunk of the accumulator)
+template <bool TMA_EPI> __host__ __device__ constexpr int conv_threads() { return 384; }
 
 template <int N_OUT, int CB, int T, bool WRES, bool TMA_EPI, int ROWS = 0>
 __global__ void __launch_bounds__(conv_threads<TMA_EPI>(), 1)
@@ -235,7 +236,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
   } else if (warp >= 4) {
     // ===================================== epilogue =====================================
     if constexpr (POOL) {
-      const int ew = warp - 4;
+      const int eg = (warp - 4) >> 2;               // which 32-channel chunk this warp pools
+      const int ew = (warp - 4) & 3;                // TMEM lane quarter
       const int OH = g.H >> 1, OW = g.W >> 1;
       const int x = ew * 32 + lane;                 // column of this thread (W == 128 == tile rows)
       const int px = x >> 1, odd = x & 1;
@@ -247,8 +249,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
         tc_fence_after();
         __nv_bfloat16* prow = out_bf + (((size_t)n * (OH + 2) + yy + 1) * (OW + 2) + px + 1) * 64;
         uint32_t* crow = mask_out + (((size_t)n * OH + yy) * OW + px) * 8;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = eg;
           float v0[32], v1[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + 0) * 64 + c * 32), v0);
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + 1) * 64 + c * 32), v1);
@@ -398,7 +400,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
       if (issuer) bulk_wait0();
       __syncwarp();
     } else {
-    const int ew = warp - 4;                      // TMEM lane quarter == warp index % 4
+    const int eg = (warp - 4) >> 2;               // this warp handles the 32-column chunks eg, eg + 2, ...
+    const int ew = (warp - 4) & 3;                // TMEM lane quarter == warp index % 4
     const int HpWp = g.Hp * g.Wp;
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
@@ -414,7 +417,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant
         const size_t o_pad = (size_t)q * N_OUT;
         const size_t o_f32 = (((size_t)n * g.H + (yp - 1)) * g.W + (xp - 1)) * N_OUT;
 #pragma unroll 1
-        for (int c = 0; c < N_OUT / 32; ++c) {
+        for (int c = eg; c < N_OUT / 32; c += 2) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
           if (valid) {
