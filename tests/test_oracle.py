@@ -92,3 +92,61 @@ def test_fp64_gradient_chain():
         e = torch.zeros(1, 8, dtype=torch.float64); e[0, i] = 1e-5
         num[i] = (f(h.detach() + e) - f(h.detach() - e)) / 2e-5
     assert (h.grad[0] - num).abs().max() / num.abs().max() < 1e-4
+
+
+def test_losses_and_metrics_hand_computed():
+    """Row L on values small enough to do by hand (homography_model.py:136-166,274-296)."""
+    pred = torch.tensor([0.0, 2.0, 0.5, -3.0, 0.0, 0.0, 0.0, 0.0, 0.0]).reshape(1, 3, 3, 1)    # 3x3: SSIM needs one window
+    tgt = torch.zeros(1, 3, 3, 1)
+    d = O.losses(None, None, pred, tgt)
+    assert "h_loss" not in d                                                   # gt-less operation (the real-data trainer)
+    assert abs(float(d["l1_loss"]) - (0 + 2 + 0.5 + 3) / 9) < 1e-7
+    assert abs(float(d["rec_loss"]) - np.sqrt((0 + 4 + 0.25 + 9) / 9)) < 1e-6
+    # Huber, delta = 1: 0.5 d^2 below 1, d - 0.5 above
+    assert abs(float(d["l1_smooth_loss"]) - (0 + 1.5 + 0.125 + 2.5) / 9) < 1e-7
+    # NCC = || x/||x|| - y/||y|| ||_2 over the whole batch tensor: identical directions -> 0, opposite -> 2
+    x = torch.tensor([3.0, 4.0]).reshape(1, 1, 2, 1)
+    assert float(O.ncc_loss(x, 2 * x)) < 1e-6 and abs(float(O.ncc_loss(x, -x)) - 2.0) < 1e-6
+    # SSIM term of a constant image against itself is 0, against its negative it saturates at 1 after the clip
+    c = torch.full((1, 5, 5, 1), 0.7, dtype=torch.float64)       # fp64: the variance terms cancel exactly
+    assert float(O.ssim_map(c, c).max()) < 1e-6 and O.ssim_map(c, c).shape == (1, 1, 3, 3)
+    assert abs(float(O.ssim_map(c, -c).mean()) - min(1.0, (1 - (-2 * 0.49 + 1e-4) / (2 * 0.49 + 1e-4)) / 2)) < 1e-5
+    # test-mode metric: sample 0 beats the identity bound, sample 1 does not (>=) and is replaced by the bound
+    gt = torch.tensor([[3.0] * 8, [1.0] * 8])
+    ph = torch.tensor([[2.0] * 8, [3.0] * 8])
+    m = O.test_metrics(ph, gt)
+    assert torch.allclose(m["batch_h_loss"], torch.tensor([1.0, 2.0])) and torch.allclose(m["h_loss_identity"], torch.tensor([3.0, 1.0]))
+    assert float(m["num_fail"]) == 1.0 and abs(float(m["bounded_h_loss"]) - (1.0 + 1.0) / 2) < 1e-7
+    assert abs(float(m["ace"]) - (np.sqrt(2.0) + 2 * np.sqrt(2.0)) / 2) < 1e-6
+    assert abs(float(O.losses(ph, gt, pred, tgt)["h_loss"]) - np.sqrt((8 * 1.0 + 8 * 4.0) / 16)) < 1e-6
+
+
+def test_transformer_grid_and_border_quirks():
+    """Row W quirks the CUDA kernels reproduce (utils/tf_spatial_transformer.py:97-139,162-177,230-240): with the identity the
+    output pixel j samples x = j*W/(W-1) (linspace(-1,1,W) endpoint mismatch), so column 0 is exact, the last column falls on
+    x = W and comes out as 0 (both taps clip to the same pixel with cancelling weights), and a vanishing t_s takes the 1e-6
+    epsilon instead of dividing by zero."""
+    Hh, W = 4, 5
+    img = torch.arange(Hh * W, dtype=torch.float64).reshape(1, Hh, W, 1) + 1.0
+    eye = torch.eye(3, dtype=torch.float64).reshape(1, 9)
+    out, _ = O.transformer(img, eye, (Hh, W))
+    assert torch.allclose(out[0, 0, 0, 0], img[0, 0, 0, 0])
+    xs = torch.arange(W, dtype=torch.float64) * W / (W - 1)
+    for j in range(W - 1):                               # interior columns: plain bilinear at x = j*W/(W-1) on row 0
+        xj = float(xs[j]); x0 = int(np.floor(xj)); f = xj - x0
+        want = (1 - f) * img[0, 0, x0, 0] + f * img[0, 0, min(x0 + 1, W - 1), 0] if x0 + 1 <= W - 1 else None
+        if want is not None:
+            assert abs(float(out[0, 0, j, 0]) - float(want)) < 1e-9
+    assert abs(float(out[0, 0, W - 1, 0])) < 1e-9 and abs(float(out[0, Hh - 1, 0, 0])) < 1e-9     # x = W / y = Hh: the "black border"
+    # t_s == 0 everywhere: the reference adds 1e-6 where |t_s| < 1e-7 -> finite output (zeros after the clip-cancellation)
+    theta = torch.tensor([[1.0, 0, 0, 0, 1, 0, 0, 0, 0]], dtype=torch.float64)
+    out0, _ = O.transformer(img, theta, (Hh, W))
+    assert torch.isfinite(out0).all()
+
+
+def test_average_grads_is_the_tower_mean():
+    """utils/utils.py:380-403 — what allreduce(sum) / N reproduces."""
+    t0 = [torch.tensor([1.0, 2.0]), torch.tensor([[4.0]])]
+    t1 = [torch.tensor([3.0, 6.0]), torch.tensor([[0.0]])]
+    avg = O.average_grads([t0, t1])
+    assert torch.equal(avg[0], torch.tensor([2.0, 4.0])) and torch.equal(avg[1], torch.tensor([[2.0]]))
