@@ -206,6 +206,13 @@ def test_adam_refreshes_fc1_mirror(udh):
     eng._mirror_current = False
     b = eng.eval_step(db)["pred_h4p"].clone()                      # converts again
     assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+    # a torch in-place write to the parameters invalidates the mirror by itself (version counter), a C-side update does not
+    eng.train_step(db)
+    assert eng._mirror_is_current()
+    eng.params.mul_(1.0)
+    assert not eng._mirror_is_current()
+    c = eng.eval_step(db)["pred_h4p"].clone()
+    assert torch.isfinite(c).all()
     fp = udh.engine.HomographyEngine(B, seed=0, numeric="fp32")
     assert fp._mirror is None
 

@@ -64,6 +64,7 @@ class HomographyEngine(object):
                                      ctypes.byref(mc), ctypes.byref(st)), "udh_cnn_fc1_mirror")
         self._mirror = (mp.value, mb.value, mc.value, st.value) if mp.value else None
         self._mirror_current = False
+        self._mirror_version = -1          # torch version counter of self.params when the mirror was written
         self.global_step = 0
         self.pg = process_group
         self.world_size = world_size
@@ -81,6 +82,12 @@ class HomographyEngine(object):
         self.dropout_seed = 0x5EED0000 + (seed or 0)
 
     # ------------------------------------------------------------------ parameters
+    def _mirror_is_current(self):
+        """The bf16 copy of fc1's weights (written by udh_adam_step_mirror) still matches self.params: libudh's kernels
+        write through raw pointers and leave torch's version counter alone, any torch in-place write to self.params
+        (copy_, add_, optimizers, checkpoint loads) bumps it and so invalidates the mirror without further bookkeeping."""
+        return self._mirror_current and self.params._version == self._mirror_version
+
     def load_flat(self, flat_np):
         self.params.copy_(torch.as_tensor(flat_np, dtype=torch.float32))
         self._mirror_current = False          # any write to self.params outside update() must clear this
@@ -203,6 +210,7 @@ class HomographyEngine(object):
                                            self.params.numel(), alpha, 0.9, 0.999, 1e-8, 1.0 / self.world_size, 1,
                                            ctypes.c_void_p(mp), mb, mc, stored, ops._stream()), "udh_adam_step_mirror")
             self._mirror_current = True
+            self._mirror_version = self.params._version
         else:
             ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, alpha, 0.9, 0.999, 1e-8,
                           1.0 / self.world_size, zero_grad=True)
@@ -214,7 +222,7 @@ class HomographyEngine(object):
         I_aug = batch["I_aug"]
         a.B, a.P, a.img_h, a.img_w, a.C = self.B, self.Pz, I_aug.shape[1], I_aug.shape[2], I_aug.shape[3]
         a.numeric_mode, a.train = self.numeric, int(train)
-        a.fwd_flags = _lib.FWD_FC1_MIRROR_CURRENT if self._mirror_current else 0
+        a.fwd_flags = _lib.FWD_FC1_MIRROR_CURRENT if self._mirror_is_current() else 0
         a.loss_type = _lib.STEP_LOSS.get(self.loss_type, -1)
         a.seed = self.dropout_seed + self.global_step
         dp = lambda t: t.data_ptr() if t is not None else None
