@@ -14,7 +14,7 @@
 //     each streamed k-block being reused by the T tiles of the item (T accumulators in TMEM);
 //   * fp32 accumulators live in TMEM (2 sets x T tiles x Cout columns): the epilogue warps drain set b while the MMA
 //     thread fills set b^1 and the TMA thread prefetches the next item's rows.
-//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-7: epilogue (TMEM lane quarters).
+//   warp 0: TMA producer | warp 1: MMA issuer | warp 2: TMEM allocator | warps 4-11: epilogue (two per TMEM lane quarter).
 //
 // Row-tile variants (W == 128, T == 2, 64 -> 64 channels: conv1_2).  ROWS = 1: forward fused with pool1; ROWS = 2: dgrad
 // with the plain bias / mask / TMA-store epilogue.  An item is the interior of two consecutive image rows (2y, 2y+1):
