@@ -35,6 +35,10 @@ extern "C" {
  * BF16: tcgen05 bf16 tensor-core tiles with fp32 TMEM accumulation, fp32 master weights — the throughput mode. */
 #define UDH_NUMERIC_FP32 0
 #define UDH_NUMERIC_BF16 1
+/* BF16X3: the same tcgen05 tiles with ERROR-COMPENSATED operands: every fp32 activation / gradient / weight travels as two
+ * 16-bit limbs (x = hi + lo) and every product is evaluated as lo.hi + hi.hi + hi.lo with fp32 TMEM accumulation, so the
+ * regressor reproduces fp32 arithmetic to ~1e-5 relative (the tensor-core parity mode; three MMA passes per product). */
+#define UDH_NUMERIC_BF16X3 2
 
 /* photometric loss selector for udh_warp_loss_bwd (reference --loss_type, homography_CNN_synthetic.py:51) */
 #define UDH_LOSS_L1 0        /* homography_model.py:328 */
@@ -171,6 +175,11 @@ int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, float alpha_
 int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                          float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin, size_t mirror_count,
                          int mirror_keep_grad, void* stream);
+/* mirror_limbs = 2 (UDH_NUMERIC_BF16X3): the mirror holds two 16-bit planes of mirror_count elements each, hi then lo,
+ * with p = hi + lo; mirror_limbs = 1 is udh_adam_step_mirror. */
+int udh_adam_step_mirror_ex(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                            float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin, size_t mirror_count,
+                            int mirror_keep_grad, int mirror_limbs, void* stream);
 /* bf16 copy of fc1's weights inside the workspace: *mirror (NULL in UDH_NUMERIC_FP32), its float range in the flat
  * parameter buffer, and whether fc1's weight gradient is stored (1) or accumulated (0) by the backward pass. */
 int udh_cnn_fc1_mirror(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void** mirror, size_t* param_begin,
@@ -245,6 +254,19 @@ int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* 
  * scratch sized by udh_debug_tc_conv_scratch_bytes. */
 int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, float* db, void* scratch, int B, int H, int W, int cin,
                        int cout, void* stream);
+/* UDH_NUMERIC_BF16X3 kernels, one layer at a time on fp32 NHWC tensors (split into limbs internally): 3x3 convolution
+ * (forward or mirrored), weight gradient, and conv1_1 (forward when out != NULL, weight gradient when g != NULL). */
+/* UDH_NUMERIC_BF16X3 workspace: write fp32 copies (hi + lo) of the saved conv / pool activations into the slots
+ * udh_cnn_activation names; *fp32_region_bytes (nullable) = size of the leading part of the workspace whose layout is common
+ * to all numeric modes (activations, dropout masks, fc buffers), so a test can run the fp32 backward on this forward state. */
+int udh_debug_x3_materialize(void* ws, size_t ws_bytes, int B, int P, size_t* fp32_region_bytes, void* stream);
+size_t udh_debug_x3_scratch_bytes(int B, int H, int W, int cin, int cout);
+int udh_debug_x3_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W, int cin,
+                      int cout, int relu, int dgrad, void* stream);
+int udh_debug_x3_wgrad(const float* x, const float* g, float* dW, float* db, void* scratch, int B, int H, int W, int cin, int cout,
+                       void* stream);
+int udh_debug_x3_conv1(const float* I1, const float* I2, const float* w, const float* bias, float* out, const float* g, float* dW,
+                       float* db, void* scratch, int B, int H, int W, void* stream);
 /* fused conv (64 -> 64 channels, W == 128) + bias + ReLU + 2x2 max-pool (conv1_2 + pool1): x [B,H,128,64] ->
  * pooled [B,H/2,64,64] fp32 and routing codes [B,H/2,64,8] uint32 (3 bits per channel, 4 = no gradient). */
 int udh_debug_tc_conv_pool(const float* x, const float* w, const float* bias, float* pooled, uint32_t* codes, void* scratch,

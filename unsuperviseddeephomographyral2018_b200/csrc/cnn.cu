@@ -61,7 +61,7 @@ struct Workspace {
     mask1 = take((size_t)B * feat);
     mask2 = take((size_t)B * 1024);
     tc = o;
-    o += (tc_workspace_bytes(B, P, numeric_mode) + 255) / 256 * 256;
+    o += ((numeric_mode == UDH_NUMERIC_BF16X3 ? x3_workspace_bytes(B, P) : tc_workspace_bytes(B, P, numeric_mode)) + 255) / 256 * 256;
     total = o;
   }
 };
@@ -72,10 +72,10 @@ inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cas
 int check_cnn_args(const char* fn, int B, int P, int numeric_mode) {
   UDH_REQUIRE(B >= 1, "%s: batch must be >= 1", fn);
   UDH_REQUIRE(P >= 128 && P % 128 == 0, "%s: patch size must be a multiple of 128 (got %d)", fn, P);
-  UDH_REQUIRE(numeric_mode == UDH_NUMERIC_FP32 || numeric_mode == UDH_NUMERIC_BF16, "%s: unknown numeric_mode %d", fn,
-              numeric_mode);
-  UDH_REQUIRE(numeric_mode != UDH_NUMERIC_BF16 || P == 128,
-              "%s: UDH_NUMERIC_BF16 is tiled for the reference's 128x128 patches (got %d); use UDH_NUMERIC_FP32", fn, P);
+  UDH_REQUIRE(numeric_mode == UDH_NUMERIC_FP32 || numeric_mode == UDH_NUMERIC_BF16 || numeric_mode == UDH_NUMERIC_BF16X3,
+              "%s: unknown numeric_mode %d", fn, numeric_mode);
+  UDH_REQUIRE(numeric_mode == UDH_NUMERIC_FP32 || P == 128,
+              "%s: the tensor-core modes are tiled for the reference's 128x128 patches (got %d); use UDH_NUMERIC_FP32", fn, P);
   return UDH_OK;
 }
 
@@ -102,7 +102,8 @@ extern "C" int udh_param_offset(int P, int tensor, size_t* offset_floats, size_t
 
 extern "C" size_t udh_cnn_workspace_bytes(int B, int P, int numeric_mode) {
   if (B < 1 || P < 128 || P % 128) return 0;
-  if (numeric_mode == UDH_NUMERIC_BF16 && P != 128) return 0;
+  if (numeric_mode != UDH_NUMERIC_FP32 && P != 128) return 0;
+  if (numeric_mode != UDH_NUMERIC_FP32 && numeric_mode != UDH_NUMERIC_BF16 && numeric_mode != UDH_NUMERIC_BF16X3) return 0;
   return Workspace(B, P, numeric_mode).total;
 }
 
@@ -111,6 +112,7 @@ extern "C" int udh_cnn_workspace_init(void* ws, size_t ws_bytes, int B, int P, i
   Workspace L(B, P, numeric_mode);
   UDH_REQUIRE(ws && ws_bytes >= L.total, "udh_cnn_workspace_init: bad workspace");
   if (numeric_mode == UDH_NUMERIC_BF16) return tc_workspace_init(ws, L.tc, B, P, as_stream(stream));
+  if (numeric_mode == UDH_NUMERIC_BF16X3) return x3_workspace_init(ws, L.tc, B, P, as_stream(stream));
   return UDH_OK;
 }
 
@@ -134,6 +136,14 @@ extern "C" int udh_cnn_activation(void* ws, size_t ws_bytes, int B, int P, int n
   return UDH_OK;
 }
 
+extern "C" int udh_debug_x3_materialize(void* ws, size_t ws_bytes, int B, int P, size_t* fp32_region_bytes, void* stream) {
+  TRY(check_cnn_args("udh_debug_x3_materialize", B, P, UDH_NUMERIC_BF16X3));
+  Workspace L(B, P, UDH_NUMERIC_BF16X3);
+  UDH_REQUIRE(ws && ws_bytes >= L.total, "udh_debug_x3_materialize: bad workspace");
+  if (fp32_region_bytes) *fp32_region_bytes = L.tc;
+  return x3_materialize_acts(ws, L.act, L.tc, B, P, as_stream(stream));
+}
+
 extern "C" int udh_cnn_fc1_mirror(void* ws, size_t ws_bytes, int B, int P, int numeric_mode, void** mirror, size_t* param_begin,
                                   size_t* count, int* grad_is_stored) {
   TRY(check_cnn_args("udh_cnn_fc1_mirror", B, P, numeric_mode));
@@ -142,8 +152,9 @@ extern "C" int udh_cnn_fc1_mirror(void* ws, size_t ws_bytes, int B, int P, int n
   ParamLayout PL(P);
   *param_begin = PL.off[16];
   *count = (size_t)(P / 8) * (P / 8) * 128 * 1024;
-  *mirror = numeric_mode == UDH_NUMERIC_BF16 ? tc_fc1_mirror(ws, L.tc, B, P) : nullptr;
-  *grad_is_stored = numeric_mode == UDH_NUMERIC_BF16 ? 1 : 0;
+  *mirror = numeric_mode == UDH_NUMERIC_BF16 ? tc_fc1_mirror(ws, L.tc, B, P)
+            : numeric_mode == UDH_NUMERIC_BF16X3 ? x3_fc1_mirror(ws, L.tc, B, P) : nullptr;
+  *grad_is_stored = numeric_mode != UDH_NUMERIC_FP32 ? 1 : 0;
   return UDH_OK;
 }
 
@@ -164,6 +175,8 @@ extern "C" int udh_cnn_fwd_ex(const float* params, const float* I1, const float*
 
   if (numeric_mode == UDH_NUMERIC_BF16) {
     TRY(tc_cnn_fwd_convs(params, PL.off, I1, I2, ws, L.act, L.tc, B, P, st));
+  } else if (numeric_mode == UDH_NUMERIC_BF16X3) {
+    TRY(x3_cnn_fwd_convs(params, PL.off, I1, I2, ws, L.act, L.tc, B, P, st));
   } else {
     // conv blocks (homography_model.py:107-118)
     const float* cur0 = I1;
@@ -197,6 +210,8 @@ extern "C" int udh_cnn_fwd_ex(const float* params, const float* I1, const float*
   UDH_CUDA(cudaMemsetAsync(at<float>(ws, L.fc1_acc), 0, (size_t)B * 1024 * 4, st));
   if (numeric_mode == UDH_NUMERIC_BF16) {
     TRY(tc_fc1_fwd(feat_in, params + PL.off[16], at<float>(ws, L.fc1_acc), ws, L.tc, B, P, (flags & UDH_FWD_FC1_MIRROR_CURRENT) != 0, st));
+  } else if (numeric_mode == UDH_NUMERIC_BF16X3) {
+    TRY(x3_fc1_fwd(feat_in, params + PL.off[16], at<float>(ws, L.fc1_acc), ws, L.tc, B, P, (flags & UDH_FWD_FC1_MIRROR_CURRENT) != 0, st));
   } else {
     TRY(sgemm_simt(feat_in, feat, 1, params + PL.off[16], 1024, 1, at<float>(ws, L.fc1_acc), 1024, B, 1024, feat,
                    B <= 256 ? 16 : 4, 0, st));
@@ -242,6 +257,8 @@ extern "C" int udh_cnn_bwd_phase(const float* params, const float* I1, const flo
   // fc1
   if (numeric_mode == UDH_NUMERIC_BF16) {
     TRY(tc_fc1_bwd(dfc1, grads + PL.off[16], gA, ws, L.tc, B, P, st));
+  } else if (numeric_mode == UDH_NUMERIC_BF16X3) {
+    TRY(x3_fc1_bwd(dfc1, grads + PL.off[16], gA, ws, L.tc, B, P, st));
   } else {
     TRY(sgemm_simt(feat_in, 1, feat, dfc1, 1024, 1, grads + PL.off[16], 1024, feat, 1024, B, 1, 1, st));  // dW1 += x^T . dfc1
     TRY(sgemm_simt(dfc1, 1024, 1, params + PL.off[16], 1, 1024, gA, feat, B, feat, 1024, 1, 0, st));   // dx = dfc1 . W1^T
@@ -254,6 +271,9 @@ extern "C" int udh_cnn_bwd_phase(const float* params, const float* I1, const flo
 
   if (numeric_mode == UDH_NUMERIC_BF16) {
     return tc_cnn_bwd_convs(params, PL.off, I1, I2, grads, gA, gB, ws, L.act, L.tc, B, P, st);
+  }
+  if (numeric_mode == UDH_NUMERIC_BF16X3) {
+    return x3_cnn_bwd_convs(params, PL.off, I1, I2, grads, gA, ws, L.tc, B, P, st);
   }
 
   // conv stack, top down.  `g` always holds the gradient w.r.t. the PRE-activation output of layer i.

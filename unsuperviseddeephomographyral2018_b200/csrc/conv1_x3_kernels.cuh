@@ -1,24 +1,19 @@
-// conv1_1 (2 -> 64 channels) on tcgen05 for the bf16 mode.  K = 3*3*2 = 18 is far below one 64-wide k-block, so the layer
-// is bound by its 277 MB bf16 output (forward) / gradient input (wgrad), not by math; the point of using the tensor pipe
-// is to get the 2.4 GMAC off the CUDA cores.  Both kernels build an explicit im2col tile in shared memory:
-//   A[128 pixels of one image row][64] bf16, k = tap*2 + plane for k < 18 (k = 18 is a constant 1 for the wgrad's bias
-//   row), zero beyond — written by 128 worker threads (thread = pixel) in the SWIZZLE_128B pattern the MMA expects.
-// forward : D[pixel][co] = A . W^T   (A K-major, W [64 co][64 k] K-major, M=128, N=64, 4 k-steps), epilogue = bias + ReLU
-//           + bf16 pack + 1-bit ReLU mask + TMA store into the zero-bordered stream — the same threads then build the
-//           next tile, so each thread alternates "drain tile i-1" / "build tile i+1" around the MMA warp.
-// wgrad   : D[k][co] += A^T . G      (the same A bytes read as an MN-major operand, M = 64; G row block by TMA;
-//           K = 128 pixels per tile, 8 k-steps), accumulated in TMEM over the CTA's whole run; row 18 is the bias gradient.
+// conv1_1 (2 -> 64 channels, K = 18) in the two-limb mode (UDH_NUMERIC_BF16X3); see conv1_tc_kernels.cuh for the design.
+// The explicit im2col row of a pixel holds BOTH limbs of its 18 taps:  k = tap*2+plane  -> hi limb,  k + 32 -> lo limb
+// (k = 18: the constant 1 of the wgrad's bias row; it has no lo limb).
+// forward : D = A . W1^T + A[:, 0:32] . W2^T  with W1[co] = [w_hi (k < 18) | w_hi (k - 32 < 18)] and W2[co] = [w_lo | 0]
+//           = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo; the epilogue splits bias + ReLU of the fp32 accumulator into limbs again.
+// wgrad   : D[k][co] += A^T . G_hi + A^T . G_lo ; rows k and k + 32 are added into the same dW row by the epilogue
+//           (x_hi.g + x_lo.g; the extra x_lo.g_lo term is harmless), row 18 is the bias gradient.
 #pragma once
-#include "tc_common.cuh"
+#include "conv1_tc_kernels.cuh"
 
 namespace udh {
 namespace tc {
 
-struct Conv1Geom { int B, H, W, tiles; };   // tiles = B*H*(W/128) row segments of 128 pixels
-
-// im2col row of pixel (n, y, x): 18 taps -> bf16, written as 3 swizzled 16-byte chunks of row `r` of `tile`
-__device__ __forceinline__ void build_im2col_row(uint8_t* tile, int r, const float* __restrict__ I1, const float* __restrict__ I2,
-                                                 int n, int y, int x, int H, int W, bool ones_col) {
+template <int FMT>
+__device__ __forceinline__ void build_im2col_row_x3(uint8_t* tile, int r, const float* __restrict__ I1, const float* __restrict__ I2,
+                                                    int n, int y, int x, int H, int W, bool ones_col) {
   float v[24];
 #pragma unroll
   for (int i = 0; i < 24; ++i) v[i] = 0.f;
@@ -40,30 +35,28 @@ __device__ __forceinline__ void build_im2col_row(uint8_t* tile, int r, const flo
   const uint32_t rowaddr = smem_u32(tile) + r * 128;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    uint32_t w[4];
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      __nv_bfloat162 p = __floats2bfloat162_rn(v[c * 8 + 2 * h], v[c * 8 + 2 * h + 1]);
-      w[h] = *reinterpret_cast<uint32_t*>(&p);
-    }
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((c ^ (r & 7)) << 4)), "r"(w[0]), "r"(w[1]),
-                 "r"(w[2]), "r"(w[3]) : "memory");
+    for (int h = 0; h < 4; ++h) split2<FMT>(v[c * 8 + 2 * h], v[c * 8 + 2 * h + 1], hi[h], lo[h]);
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)((c ^ (r & 7)) << 4)), "r"(hi[0]), "r"(hi[1]),
+                 "r"(hi[2]), "r"(hi[3]) : "memory");
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + (uint32_t)(((4 + c) ^ (r & 7)) << 4)), "r"(lo[0]), "r"(lo[1]),
+                 "r"(lo[2]), "r"(lo[3]) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------- forward
-// 160 threads: warps 0-3 workers (thread = pixel = TMEM lane), warp 4 = TMEM alloc + MMA issuer.  The workers are
-// instruction-bound (im2col build + 64-channel epilogue per pixel), so several CTAs share an SM (kConv1CtasPerSm).
-constexpr int kConv1CtasPerSm = 3;
-static __global__ void __launch_bounds__(160, kConv1CtasPerSm)
-conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g, const float* __restrict__ I1,
+constexpr int kConv1X3CtasPerSm = 3;
+template <int FMT>
+__global__ void __launch_bounds__(160, kConv1X3CtasPerSm)
+conv1_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g, const float* __restrict__ I1,
                     const float* __restrict__ I2, const float* __restrict__ w, const float* __restrict__ bias,
                     uint32_t* __restrict__ mask_out) {
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                       // [2][128][128 B]
-  uint8_t* sW = base + 2 * 16384;           // [64 co][128 B]
-  uint8_t* sEpi = sW + 8192;                // [4 warps][32][128 B]
+  uint8_t* sW = base + 2 * 16384;           // W1, W2: [64 co][128 B] each
+  uint8_t* sEpi = sW + 16384;               // [4 warps][32][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 16384);
   uint64_t* a_full = bars;                  // [2] count 128 (workers)
   uint64_t* a_empty = bars + 2;             // [2] count 1 (MMA commit)
@@ -72,19 +65,23 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // zero both A tiles (columns 24..63 stay zero for ever) and build the weight tile W[co][k] = w[tap][ci][co], k = tap*2+ci
+  // zero both A tiles (the unused columns stay zero for ever) and build the two weight tiles
   for (int i = threadIdx.x; i < 2 * 16384 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
     const int co = i >> 3, c = i & 7;       // chunk c holds k = 8c .. 8c+7
-    uint32_t pk[4];
+    uint32_t p1[4], p2[4];
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const int k0 = c * 8 + 2 * h;
-      const float f0 = k0 < 18 ? __ldg(w + k0 * 64 + co) : 0.f, f1 = k0 + 1 < 18 ? __ldg(w + (k0 + 1) * 64 + co) : 0.f;
-      __nv_bfloat162 p = __floats2bfloat162_rn(f0, f1);
-      pk[h] = *reinterpret_cast<uint32_t*>(&p);
+      const int kk = c < 4 ? k0 : k0 - 32;  // tap index this column multiplies (hi columns 0.., lo columns 32..)
+      const float f0 = kk < 18 ? __ldg(w + kk * 64 + co) : 0.f, f1 = kk + 1 < 18 ? __ldg(w + (kk + 1) * 64 + co) : 0.f;
+      uint32_t hi, lo;
+      split2<FMT>(f0, f1, hi, lo);
+      p1[h] = hi;
+      p2[h] = c < 4 ? lo : 0u;
     }
-    *reinterpret_cast<uint4*>(sW + co * 128 + ((c ^ (co & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(sW + co * 128 + ((c ^ (co & 7)) << 4)) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(sW + 8192 + co * 128 + ((c ^ (co & 7)) << 4)) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
@@ -116,7 +113,7 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
         const int n = row / g.H, y = row - n * g.H;
         const int b = i & 1;
         mbar_wait(&a_empty[b], ((i >> 1) & 1) ^ 1);
-        build_im2col_row(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, false);
+        build_im2col_row_x3<FMT>(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, false);
         fence_proxy_async();
         mbar_arrive(&a_full[b]);
       }
@@ -129,8 +126,8 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
         const int q0w = (n * (g.H + 2) + y + 1) * (g.W + 2) + 1 + seg * 128 + warp * 32;    // padded position of this warp's first pixel
         mbar_wait(&t_full[b], (j >> 1) & 1);
         tc_fence_after();
-        if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); store_pending = false; }
         uint32_t mo[2];
+        uint32_t hi[2][16], lo[2][16];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float v[32];
@@ -146,29 +143,36 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
           for (int k = 0; k < 32; ++k) mw |= (v[k] > 0.f ? 1u : 0u) << k;
           mo[c] = mw;
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j4 * 8 + 0], v[j4 * 8 + 1]), p1 = __floats2bfloat162_rn(v[j4 * 8 + 2], v[j4 * 8 + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j4 * 8 + 4], v[j4 * 8 + 5]), p3 = __floats2bfloat162_rn(v[j4 * 8 + 6], v[j4 * 8 + 7]);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)(((c * 4 + j4) ^ sw) << 4)),
-                         "r"(*reinterpret_cast<uint32_t*>(&p0)), "r"(*reinterpret_cast<uint32_t*>(&p1)),
-                         "r"(*reinterpret_cast<uint32_t*>(&p2)), "r"(*reinterpret_cast<uint32_t*>(&p3)) : "memory");
-          }
+          for (int k = 0; k < 16; ++k) split2<FMT>(v[2 * k], v[2 * k + 1], hi[c][k], lo[c][k]);
         }
         tc_fence_before();
         mbar_arrive(&t_empty[b]);
         if (mask_out) *reinterpret_cast<uint2*>(mask_out + (size_t)(q0w + lane) * 2) = make_uint2(mo[0], mo[1]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) { tma_store_2d(&tmOut, stg, 0, q0w); bulk_commit(); }
-        store_pending = true;
+#pragma unroll
+        for (int limb = 0; limb < 2; ++limb) {
+          if (store_pending) { if (lane == 0) bulk_wait_read0(); __syncwarp(); }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t* s = limb ? lo[c] : hi[c];
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (uint32_t)(((c * 4 + j4) ^ sw) << 4)),
+                           "r"(s[j4 * 4]), "r"(s[j4 * 4 + 1]), "r"(s[j4 * 4 + 2]), "r"(s[j4 * 4 + 3]) : "memory");
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmOut, stg, limb * 64, q0w); bulk_commit(); }
+          store_pending = true;
+        }
       }
     }
     if (lane == 0) bulk_wait0();
     __syncwarp();
   } else {
     // ---- MMA issuer (whole warp converged)
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
-    const uint32_t w_lo = desc_lo(smem_u32(sW), 16);
+    constexpr uint32_t idesc = make_idesc_f16kind(128, 64, 0, 0, FMT, FMT);
+    const uint32_t w1_lo = desc_lo(smem_u32(sW), 16), w2_lo = desc_lo(smem_u32(sW + 8192), 16);
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
       const uint32_t ph = (i >> 1) & 1;
@@ -178,8 +182,11 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
       const uint32_t a_lo = desc_lo(smem_u32(sA + b * 16384), 16);
       if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 2; ++k)            // k-steps 0,1 cover k = 0..31; everything beyond 18 is zero
-          umma_bf16(tmem_base + (uint32_t)(b * 64), desc_from_lo(a_lo + k * 2), desc_from_lo(w_lo + k * 2), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)            // all 64 columns against W1: hi.w_hi (k-steps 0,1) + lo.w_hi (k-steps 2,3)
+          umma_bf16(tmem_base + (uint32_t)(b * 64), desc_from_lo(a_lo + k * 2), desc_from_lo(w1_lo + k * 2), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 2; ++k)            // hi columns against W2: hi.w_lo
+          umma_bf16(tmem_base + (uint32_t)(b * 64), desc_from_lo(a_lo + k * 2), desc_from_lo(w2_lo + k * 2), idesc, 1u);
         umma_commit(&a_empty[b]);
         umma_commit(&t_full[b]);
       }
@@ -192,15 +199,16 @@ conv1_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
 }
 
 // ------------------------------------------------------------------------------------------------------------- wgrad
-// 160 threads: warps 0-3 build im2col tiles (+ the constant-one column 18), warp 4 = TMA (G rows) + TMEM alloc + MMA issuer.
-static __global__ void __launch_bounds__(160, kConv1CtasPerSm)
-conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g, const float* __restrict__ I1,
+constexpr int kConv1X3WgradCtasPerSm = 2;
+template <int FMT_X, int FMT_G>
+__global__ void __launch_bounds__(160, kConv1X3WgradCtasPerSm)
+conv1_x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g, const float* __restrict__ I1,
                       const float* __restrict__ I2, float* __restrict__ dW, float* __restrict__ db) {
   extern __shared__ uint8_t raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                       // [2][128][128 B]
-  uint8_t* sG = base + 2 * 16384;           // [2][128][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 2 * 16384);
+  uint8_t* sG = base + 2 * 16384;           // [2 stages][2 limbs][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 4 * 16384);
   uint64_t* a_full = bars;                  // [2] count 128
   uint64_t* g_full = bars + 2;              // [2] TMA
   uint64_t* empty = bars + 4;               // [2] MMA commit
@@ -221,7 +229,7 @@ conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                  // predecessor grid complete (the prologue above touched only parameters, written long before)
+  pdl_wait();
   pdl_trigger();
   const int my_tiles = (g.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int segs = g.W / 128;
@@ -234,28 +242,30 @@ conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g
       const int n = row / g.H, y = row - n * g.H;
       const int b = i & 1;
       mbar_wait(&empty[b], ((i >> 1) & 1) ^ 1);
-      build_im2col_row(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, true);
+      build_im2col_row_x3<FMT_X>(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, true);
       fence_proxy_async();
       mbar_arrive(&a_full[b]);
     }
     if (my_tiles > 0) {
-      // epilogue: M = 64 accumulator rows live in lanes 32*(r/16) + r%16; rows 0..17 = dW[k][co], row 18 = db[co]
+      // epilogue: M = 64 accumulator rows live in lanes 32*(r/16) + r%16; rows 0..17 (x_hi) and 32..49 (x_lo) = dW[k][co],
+      // row 18 = db[co]
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const int r = warp * 16 + lane;        // valid for lane < 16
+      const int rr = r & 31;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        if (lane < 16 && r <= 18) {
-          float* dst = r < 18 ? dW + r * 64 + c * 32 : db + c * 32;
+        if (lane < 16 && (rr < 18 || r == 18)) {
+          float* dst = rr < 18 ? dW + rr * 64 + c * 32 : db + c * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) red_add_v4(dst + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       }
     }
   } else {
-    constexpr uint32_t idesc = make_idesc_bf16(64, 64, 1, 1);
+    constexpr uint32_t idesc = make_idesc_f16kind(64, 64, 1, 1, FMT_X, FMT_G);
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const int seg = tile % segs, row = tile / segs;
@@ -265,18 +275,23 @@ conv1_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const Conv1Geom g
       const uint32_t ph = (i >> 1) & 1;
       mbar_wait(&empty[b], ph ^ 1);                                  // both tiles of the stage are free again
       if (elect_one()) {
-        mbar_arrive_expect_tx(&g_full[b], 16384);
-        tma_load_2d(sG + b * 16384, &tmG, 0, q0, &g_full[b]);
+        mbar_arrive_expect_tx(&g_full[b], 2 * 16384);
+        tma_load_2d(sG + b * 32768, &tmG, 0, q0, &g_full[b]);
+        tma_load_2d(sG + b * 32768 + 16384, &tmG, 64, q0, &g_full[b]);
       }
       __syncwarp();
       mbar_wait(&a_full[b], ph);
       mbar_wait(&g_full[b], ph);
       tc_fence_after();
-      const uint32_t a_lo = desc_lo(smem_u32(sA + b * 16384), 16384), g_lo = desc_lo(smem_u32(sG + b * 16384), 16384);
+      const uint32_t a_lo = desc_lo(smem_u32(sA + b * 16384), 16384);
+      const uint32_t gh_lo = desc_lo(smem_u32(sG + b * 32768), 16384), gl_lo = desc_lo(smem_u32(sG + b * 32768 + 16384), 16384);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_bf16(tmem_base, desc_from_lo(a_lo + kk * 128), desc_from_lo(g_lo + kk * 128), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16(tmem_base, desc_from_lo(a_lo + kk * 128), desc_from_lo(gh_lo + kk * 128), idesc, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(tmem_base, desc_from_lo(a_lo + kk * 128), desc_from_lo(gl_lo + kk * 128), idesc, 1u);
         umma_commit(&empty[b]);
       }
       __syncwarp();

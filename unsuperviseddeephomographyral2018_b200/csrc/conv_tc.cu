@@ -8,58 +8,14 @@
 #include "wgrad_tc_kernels.cuh"
 #include "gemm_tc_kernels.cuh"
 #include "conv1_tc_kernels.cuh"
+#include "tc_layout.cuh"
 
 namespace udh {
 
 namespace {
 
-struct ConvSpec { int cin, cout, div; };
-const ConvSpec kConv[8] = {{2, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 2}, {64, 128, 4}, {128, 128, 4}, {128, 128, 8}, {128, 128, 8}};
-
-inline size_t al256(size_t n) { return (n + 255) / 256 * 256; }
-inline unsigned grid1d(size_t want, size_t cap) { return (unsigned)(want < cap ? (want ? want : 1) : cap); }
-
-// byte offsets inside the tensor-core region of the workspace
-struct TcLayout {
-  size_t P[11];      // padded bf16 activations: 0..7 conv outputs, 8..10 pool outputs
-  size_t G[11];      // padded bf16 gradients w.r.t. the same tensors (pre-activation for convs)
-  size_t numel[11];  // padded element counts
-  size_t wf[8], wd[8];   // packed bf16 weights, forward / dgrad (rotated)
-  size_t Mb[8];      // 1-bit ReLU masks [Q][C/32] uint32 of the conv outputs a dgrad needs (layers 0, 2, 4, 6)
-  size_t Px[3];      // max-pool routing codes [B][H/2][W/2][C/8] uint32 (3 bits per channel), written by the forward
-  size_t fc_x, fc_w, fc_dy;   // bf16 copies for the fc1 GEMMs: x [B,F], W [F,1024], dy [B,1024]
-  size_t total;
-  TcLayout(int B, int P_) {
-    size_t o = 0;
-    auto take = [&](size_t bytes) { size_t r = o; o += al256(bytes); return r; };
-    for (int i = 0; i < 8; ++i) {
-      const size_t s = P_ / kConv[i].div + 2;
-      numel[i] = (size_t)B * s * s * kConv[i].cout;
-    }
-    numel[8] = (size_t)B * (P_ / 2 + 2) * (P_ / 2 + 2) * 64;
-    numel[9] = (size_t)B * (P_ / 4 + 2) * (P_ / 4 + 2) * 64;
-    numel[10] = (size_t)B * (P_ / 8 + 2) * (P_ / 8 + 2) * 128;
-    for (int i = 0; i < 11; ++i) P[i] = take(numel[i] * 2);
-    for (int i = 0; i < 11; ++i) G[i] = take(numel[i] * 2);
-    for (int i = 0; i < 8; ++i) { wf[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); wd[i] = take((size_t)9 * kConv[i].cin * kConv[i].cout * 2); }
-    for (int i = 0; i < 8; ++i) Mb[i] = (i % 2 == 0) ? take(numel[i] / 8) : 0;
-    for (int i = 0; i < 3; ++i) Px[i] = take((size_t)B * (P_ >> (i + 1)) * (P_ >> (i + 1)) * (i == 2 ? 16 : 8) * 4);
-    const size_t feat = (size_t)(P_ / 8) * (P_ / 8) * 128;
-    fc_x = take((size_t)B * feat * 2);
-    fc_w = take(feat * 1024 * 2);
-    fc_dy = take((size_t)B * 1024 * 2);
-    total = o;
-  }
-};
-
-template <typename T>
-inline T* at(void* ws, size_t off) { return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off); }
-
-#define TRY(call)                    \
-  do {                               \
-    int rc__ = (call);               \
-    if (rc__ != UDH_OK) return rc__; \
-  } while (0)
+using namespace tcl;
+#define TRY UDH_TRY
 
 // ---------------------------------------------------------------------------------------------------- small kernels
 // dst[tap][cb][n][k] bf16 <- fp32 HWIO w[tap][ci][co].
@@ -444,38 +400,6 @@ int cast_bf16(const float* src, __nv_bfloat16* dst, size_t n, cudaStream_t st) {
   return check_launch("cast_bf16");
 }
 
-// C[M][N] (+)= A . B on tensor cores.  a_inner/a_outer: dims of A's tensor (innermost first); same for B.
-template <bool A_MN, bool B_MN, bool ATOMIC>
-int launch_gemm(const __nv_bfloat16* A, uint64_t a_inner, uint64_t a_outer, const __nv_bfloat16* Bm, uint64_t b_inner, uint64_t b_outer,
-                float* C, int64_t ldc, int M, int N, int K, int k_splits, cudaStream_t st) {
-  tc::GemmGeom g;
-  g.M = M; g.N = N; g.ldc = ldc;
-  g.m_tiles = (M + 127) / 128; g.n_tiles = (N + 255) / 256;
-  const int kb = (K + 63) / 64;
-  g.k_splits = k_splits;
-  g.kb_per_split = (kb + k_splits - 1) / k_splits;
-  UDH_REQUIRE(g.kb_per_split * k_splits == kb, "tc gemm: k-blocks (%d) must divide evenly into %d splits", kb, k_splits);
-  CUtensorMap tmA, tmB;
-  uint64_t dA[2] = {a_inner, a_outer}, sA[2] = {2, a_inner * 2};
-  uint32_t boxA[2] = {64, A_MN ? 64u : 128u};
-  TRY(tc::make_tmap_bf16(&tmA, A, 2, dA, sA, boxA));
-  uint64_t dB[2] = {b_inner, b_outer}, sB[2] = {2, b_inner * 2};
-  uint32_t boxB[2] = {64, B_MN ? 64u : 256u};
-  TRY(tc::make_tmap_bf16(&tmB, Bm, 2, dB, sB, boxB));
-  // output map for the TMA-store epilogue: fp32 [M][ldc], box = 32 floats (128 B) x 32 rows
-  CUtensorMap tmC;
-  uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[2] = {4, (uint64_t)ldc * 4};
-  uint32_t boxC[2] = {32, 32};
-  TRY(tc::make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, 2, dC, sC, boxC));
-  const size_t smem = 1024 + (size_t)tc::kGemmStages * tc::kGemmStageBytes + (ATOMIC ? 0 : tc::kGemmEpiBytes) + 256;
-  auto kern = tc::tc_gemm_kernel<A_MN, B_MN, ATOMIC>;
-  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int sms = persistent_ctas();
-  const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
-  launch_chain(kern, dim3(tiles < sms ? tiles : sms), dim3(256), smem, st, tmA, tmB, tmC, g, C);
-  return check_launch("tc_gemm_kernel");
-}
-
 // conv1_1 on the tensor pipe (im2col tile built in shared memory), see conv1_tc_kernels.cuh
 int conv1_tc_fwd(const float* I1, const float* I2, const float* w, const float* bias, __nv_bfloat16* out_pad, uint32_t* mask_out, int B,
                  int H, int W, cudaStream_t st) {
@@ -510,9 +434,6 @@ int conv1_tc_wgrad(const float* I1, const float* I2, const __nv_bfloat16* G_pad,
   launch_chain(tc::conv1_tc_wgrad_kernel, dim3(grid), dim3(160), smem, st, tmG, g, I1, I2, dW, db);
   return check_launch("conv1_tc_wgrad_kernel");
 }
-
-// input tensor index (into P / G) of conv layer i (i >= 1)
-inline int input_of(int i) { return (i == 2 || i == 4 || i == 6) ? 8 + (i - 2) / 2 : i - 1; }
 
 }  // namespace
 
@@ -640,7 +561,7 @@ int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_o
   const int kb = (int)(feat / 64);
   int splits = 32;
   while (kb % splits) splits >>= 1;
-  return launch_gemm<false, true, true>(xb, feat, (uint64_t)B, wb, 1024, feat, acc, 1024, B, 1024, (int)feat, splits, st);
+  return tc::launch_gemm<false, true, true>(xb, feat, (uint64_t)B, wb, 1024, feat, acc, 1024, B, 1024, (int)feat, splits, nullptr, st);
 }
 
 // fc1 backward: dW[F,1024] = x^T . dy (stored: the gradient buffer is zero on entry), dx[B,F] = dy . W^T.
@@ -653,8 +574,8 @@ int tc_fc1_bwd(const float* dy, float* dW, float* dx, void* ws, size_t tc_off, i
   __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_w);
   __nv_bfloat16* dyb = reinterpret_cast<__nv_bfloat16*>(tcw + L.fc_dy);
   TRY(cast_bf16(dy, dyb, (size_t)B * 1024, st));
-  TRY((launch_gemm<true, true, false>(xb, feat, (uint64_t)B, dyb, 1024, (uint64_t)B, dW, 1024, (int)feat, 1024, B, 1, st)));
-  return launch_gemm<false, false, false>(dyb, 1024, (uint64_t)B, wb, 1024, feat, dx, (int64_t)feat, B, (int)feat, 1024, 1, st);
+  TRY((tc::launch_gemm<true, true, false>(xb, feat, (uint64_t)B, dyb, 1024, (uint64_t)B, dW, 1024, (int)feat, 1024, B, 1, nullptr, st)));
+  return tc::launch_gemm<false, false, false>(dyb, 1024, (uint64_t)B, wb, 1024, feat, dx, (int64_t)feat, B, (int)feat, 1024, 1, nullptr, st);
 }
 
 // Debug / test entry: one tensor-core conv layer on fp32 NHWC tensors (pads + casts internally).

@@ -24,4 +24,16 @@ int tc_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_o
 void* tc_fc1_mirror(void* ws, size_t tc_off, int B, int P);
 int tc_fc1_bwd(const float* dy, float* dW, float* dx, void* ws, size_t tc_off, int B, int P, cudaStream_t st);
 
+// ---- UDH_NUMERIC_BF16X3 (conv_x3.cu): the same pipeline on two-limb streams, lo.hi + hi.hi + hi.lo per product ----------
+size_t x3_workspace_bytes(int B, int P);
+int x3_workspace_init(void* ws, size_t tc_off, int B, int P, cudaStream_t st);
+int x3_cnn_fwd_convs(const float* params, const size_t* param_off, const float* I1, const float* I2, void* ws,
+                     const size_t* act_off, size_t tc_off, int B, int P, cudaStream_t st);
+int x3_cnn_bwd_convs(const float* params, const size_t* param_off, const float* I1, const float* I2, float* grads, float* gA,
+                     void* ws, size_t tc_off, int B, int P, cudaStream_t st);
+int x3_fc1_fwd(const float* x, const float* w, float* acc, void* ws, size_t tc_off, int B, int P, bool w_mirror_current, cudaStream_t st);
+void* x3_fc1_mirror(void* ws, size_t tc_off, int B, int P);
+int x3_materialize_acts(void* ws, const size_t* act_off, size_t tc_off, int B, int P, cudaStream_t st);
+int x3_fc1_bwd(const float* dy, float* dW, float* dx, void* ws, size_t tc_off, int B, int P, cudaStream_t st);
+
 }  // namespace udh

@@ -12,10 +12,16 @@
 namespace udh {
 namespace tc {
 
+// The contraction may run over up to three SEGMENTS: segment s reads A at (k + a_koff[s], m + a_moff[s]) and B at
+// (k + b_koff[s], n + b_noff[s]).  The two-limb mode (UDH_NUMERIC_BF16X3) uses this to evaluate
+// lo.hi + hi.hi + hi.lo over operands stored as [hi | lo] without duplicating anything in memory; one segment with zero
+// offsets is the plain GEMM.
 struct GemmGeom {
   int M, N;            // logical output size (rows beyond M / cols beyond N are not stored)
   int m_tiles, n_tiles, k_splits;
-  int kb_per_split;    // k-blocks (of 64) per split
+  int kb_per_split;    // k-blocks (of 64) per split, counted over all segments
+  int kb_per_seg;      // k-blocks of one segment
+  int a_koff[3], a_moff[3], b_koff[3], b_noff[3];
   int64_t ldc;
 };
 
@@ -26,7 +32,7 @@ constexpr int kGemmEpiBytes = 2 * 4 * 32 * 128;  // TMA-store staging of the non
 
 // ATOMIC: split-K partial tiles are added with 16-byte vector reductions.  Otherwise the tile is stored through a swizzled
 // shared-memory staging block and TMA (full 128-byte lines; rows / columns beyond M / N are clipped by the tensor map).
-template <bool A_MN, bool B_MN, bool ATOMIC>
+template <bool A_MN, bool B_MN, bool ATOMIC, int FMT_A = kFmtBF16, int FMT_B = kFmtBF16>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                const GemmGeom g, float* __restrict__ C) {
@@ -71,27 +77,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode((int)blockIdx.x + i * (int)gridDim.x, mt, nt, ks);
         for (int kb = 0; kb < g.kb_per_split; ++kb, ++cnt) {
           const int s = cnt % kGemmStages;
-          const int k0 = (ks * g.kb_per_split + kb) * 64;
+          const int kg = ks * g.kb_per_split + kb;
+          const int seg = kg / g.kb_per_seg;
+          const int k0 = (kg - seg * g.kb_per_seg) * 64;
+          const int ak = k0 + g.a_koff[seg], am = mt * 128 + g.a_moff[seg], bk = k0 + g.b_koff[seg], bn = nt * 256 + g.b_noff[seg];
           mbar_wait(&empty[s], ((cnt / kGemmStages) & 1) ^ 1);
           mbar_arrive_expect_tx(&full[s], kGemmStageBytes);
           uint8_t* sa = base + (size_t)s * kGemmStageBytes;
           uint8_t* sb = sa + 16384;
           if (A_MN) {
-            for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * 8192, &tmA, mt * 128 + j * 64, k0, &full[s]);
+            for (int j = 0; j < 2; ++j) tma_load_2d(sa + j * 8192, &tmA, am + j * 64, ak, &full[s]);
           } else {
-            tma_load_2d(sa, &tmA, k0, mt * 128, &full[s]);
+            tma_load_2d(sa, &tmA, ak, am, &full[s]);
           }
           if (B_MN) {
-            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 8192, &tmB, nt * 256 + j * 64, k0, &full[s]);
+            for (int j = 0; j < 4; ++j) tma_load_2d(sb + j * 8192, &tmB, bn + j * 64, bk, &full[s]);
           } else {
-            tma_load_2d(sb, &tmB, k0, nt * 256, &full[s]);
+            tma_load_2d(sb, &tmB, bk, bn, &full[s]);
           }
         }
       }
     }
   } else if (warp == 1) {
     // whole warp converged; one elected lane issues
-    constexpr uint32_t idesc = make_idesc_bf16(128, 256, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc_f16kind(128, 256, A_MN ? 1 : 0, B_MN ? 1 : 0, FMT_A, FMT_B);
     uint32_t cnt = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
@@ -169,6 +178,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Host launcher.  C[M][N] (+)= A . B on tensor cores.  a_inner/a_outer: dims of A's tensor (innermost first); same for B.
+// seg (nullable): offsets of the contraction segments (see GemmGeom), K is the length of ONE segment.
+struct GemmSegments { int n; int a_koff[3], a_moff[3], b_koff[3], b_noff[3]; };
+
+template <bool A_MN, bool B_MN, bool ATOMIC, int FMT_A = kFmtBF16, int FMT_B = kFmtBF16>
+inline int launch_gemm(const void* A, uint64_t a_inner, uint64_t a_outer, const void* Bm, uint64_t b_inner, uint64_t b_outer,
+                       float* C, int64_t ldc, int M, int N, int K, int k_splits, const GemmSegments* seg, cudaStream_t st) {
+  GemmGeom g;
+  g.M = M; g.N = N; g.ldc = ldc;
+  g.m_tiles = (M + 127) / 128; g.n_tiles = (N + 255) / 256;
+  const int nseg = seg ? seg->n : 1;
+  g.kb_per_seg = (K + 63) / 64;
+  const int kb = g.kb_per_seg * nseg;
+  g.k_splits = k_splits;
+  g.kb_per_split = (kb + k_splits - 1) / k_splits;
+  UDH_REQUIRE(g.kb_per_split * k_splits == kb, "tc gemm: k-blocks (%d) must divide evenly into %d splits", kb, k_splits);
+  for (int i = 0; i < 3; ++i) {
+    g.a_koff[i] = seg && i < nseg ? seg->a_koff[i] : 0; g.a_moff[i] = seg && i < nseg ? seg->a_moff[i] : 0;
+    g.b_koff[i] = seg && i < nseg ? seg->b_koff[i] : 0; g.b_noff[i] = seg && i < nseg ? seg->b_noff[i] : 0;
+  }
+  CUtensorMap tmA, tmB;
+  uint64_t dA[2] = {a_inner, a_outer}, sA[2] = {2, a_inner * 2};
+  uint32_t boxA[2] = {64, A_MN ? 64u : 128u};
+  int rc = make_tmap_bf16(&tmA, A, 2, dA, sA, boxA);
+  if (rc != UDH_OK) return rc;
+  uint64_t dB[2] = {b_inner, b_outer}, sB[2] = {2, b_inner * 2};
+  uint32_t boxB[2] = {64, B_MN ? 64u : 256u};
+  rc = make_tmap_bf16(&tmB, Bm, 2, dB, sB, boxB);
+  if (rc != UDH_OK) return rc;
+  // output map for the TMA-store epilogue: fp32 [M][ldc], box = 32 floats (128 B) x 32 rows
+  CUtensorMap tmC;
+  uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[2] = {4, (uint64_t)ldc * 4};
+  uint32_t boxC[2] = {32, 32};
+  rc = make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, C, 2, dC, sC, boxC);
+  if (rc != UDH_OK) return rc;
+  const size_t smem = 1024 + (size_t)kGemmStages * kGemmStageBytes + (ATOMIC ? 0 : kGemmEpiBytes) + 256;
+  auto kern = tc_gemm_kernel<A_MN, B_MN, ATOMIC, FMT_A, FMT_B>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = persistent_ctas();
+  const int tiles = g.m_tiles * g.n_tiles * g.k_splits;
+  launch_chain(kern, dim3(tiles < sms ? tiles : sms), dim3(256), smem, st, tmA, tmB, tmC, g, C);
+  return check_launch("tc_gemm_kernel");
 }
 
 }  // namespace tc

@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "x3_config.cuh"
 
 namespace udh {
 
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) h4p_loss_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, float alpha, float b1, float b2,
                                                    float eps, float gs, int zero_grad, uint2* __restrict__ mirror,
-                                                   size_t mb4, size_t me4, int keep_grad) {
+                                                   size_t mb4, size_t me4, int keep_grad, uint2* __restrict__ mirror_lo) {
   pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   const float c1 = 1.0f - b1, c2 = 1.0f - b2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -109,9 +110,17 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, float
     p[i] = pv; m[i] = mv; v[i] = vv;
     const bool in_mirror = i >= mb4 && i < me4;
     if (in_mirror) {
-      const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
-      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      mirror[i - mb4] = pk;
+      if (mirror_lo) {             // two-limb mirror (UDH_NUMERIC_BF16X3): p = hi + lo
+        uint2 h, l;
+        tc::split2<kX3Fwd>(pv.x, pv.y, h.x, l.x);
+        tc::split2<kX3Fwd>(pv.z, pv.w, h.y, l.y);
+        mirror[i - mb4] = h;
+        mirror_lo[i - mb4] = l;
+      } else {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(pv.x, pv.y), hi = __floats2bfloat162_rn(pv.z, pv.w);
+        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        mirror[i - mb4] = pk;
+      }
     }
     if (zero_grad && !(in_mirror && keep_grad)) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -185,6 +194,14 @@ extern "C" int udh_adam_step(float* p, float* g, float* m, float* v, size_t n, f
 extern "C" int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
                                     float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin,
                                     size_t mirror_count, int mirror_keep_grad, void* stream) {
+  return udh_adam_step_mirror_ex(p, g, m, v, n, alpha_t, beta1, beta2, eps, grad_scale, zero_grad, mirror, mirror_begin, mirror_count,
+                                 mirror_keep_grad, 1, stream);
+}
+
+extern "C" int udh_adam_step_mirror_ex(float* p, float* g, float* m, float* v, size_t n, float alpha_t, float beta1, float beta2,
+                                       float eps, float grad_scale, int zero_grad, void* mirror, size_t mirror_begin,
+                                       size_t mirror_count, int mirror_keep_grad, int mirror_limbs, void* stream) {
+  UDH_REQUIRE(mirror_limbs == 1 || mirror_limbs == 2, "udh_adam_step_mirror_ex: mirror_limbs must be 1 or 2");
   UDH_REQUIRE(p && g && m && v, "udh_adam_step: null pointer");
   if (!mirror) mirror_begin = mirror_count = 0;
   UDH_REQUIRE(mirror_begin % 4 == 0 && mirror_count % 4 == 0 && mirror_begin + mirror_count <= n && (uintptr_t)mirror % 8 == 0,
@@ -197,6 +214,7 @@ extern "C" int udh_adam_step_mirror(float* p, float* g, float* m, float* v, size
   udh::ProfScope ps(udh::PROF_ADAM, udh::as_stream(stream));
   udh::launch_chain(udh::adam_kernel, dim3(blocks), dim3(256), 0, udh::as_stream(stream), (float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
                                                               beta1, beta2, eps, grad_scale, zero_grad, (uint2*)mirror,
-                                                              mirror_begin / 4, (mirror_begin + mirror_count) / 4, mirror_keep_grad);
+                                                              mirror_begin / 4, (mirror_begin + mirror_count) / 4, mirror_keep_grad,
+                                                              (mirror && mirror_limbs == 2) ? (uint2*)((char*)mirror + mirror_count * 2) : (uint2*)nullptr);
   return udh::check_launch("udh_adam_step");
 }

@@ -18,7 +18,7 @@ from ._lib import check, lib
 LOSS_TYPES = ("h_loss", "rec_loss", "ssim_loss", "l1_loss", "l1_smooth_loss", "ncc_loss")
 _PHOTO_BWD = {"l1_loss": _lib.LOSS_L1, "rec_loss": _lib.LOSS_REC, "l1_smooth_loss": _lib.LOSS_L1_SMOOTH, "ncc_loss": _lib.LOSS_NCC,
               "ssim_loss": _lib.LOSS_CUSTOM}
-NUMERIC = {"fp32": _lib.NUMERIC_FP32, "bf16": _lib.NUMERIC_BF16}
+NUMERIC = {"fp32": _lib.NUMERIC_FP32, "bf16": _lib.NUMERIC_BF16, "bf16x3": _lib.NUMERIC_BF16X3}
 
 
 def decay_steps(lr, min_lr, num_total_steps=150000, decay_rate=0.96):
@@ -101,7 +101,7 @@ class HomographyEngine(object):
     def export_named(self, path):
         """Parameters under the reference's TF-Slim variable names / shapes (+ global_step)."""
         import numpy as np
-        P.save_named_npz(path, self.params.cpu().numpy(), extra={"global_step": np.array(self.global_step)})
+        P.save_named_npz(path, self.params.cpu().numpy(), extra={"global_step": np.array(self.global_step)}, patch_size=self.Pz)
 
     def import_named(self, path):
         self.load_flat(P.load_named_npz(path, self.Pz))
@@ -206,9 +206,10 @@ class HomographyEngine(object):
         alpha = lr_t * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
         if self._mirror is not None:
             mp, mb, mc, stored = self._mirror
-            check(lib.udh_adam_step_mirror(self._p(self.params), self._p(self.grads), self._p(self.adam_m), self._p(self.adam_v),
-                                           self.params.numel(), alpha, 0.9, 0.999, 1e-8, 1.0 / self.world_size, 1,
-                                           ctypes.c_void_p(mp), mb, mc, stored, ops._stream()), "udh_adam_step_mirror")
+            limbs = 2 if self.numeric == _lib.NUMERIC_BF16X3 else 1
+            check(lib.udh_adam_step_mirror_ex(self._p(self.params), self._p(self.grads), self._p(self.adam_m), self._p(self.adam_v),
+                                              self.params.numel(), alpha, 0.9, 0.999, 1e-8, 1.0 / self.world_size, 1,
+                                              ctypes.c_void_p(mp), mb, mc, stored, limbs, ops._stream()), "udh_adam_step_mirror_ex")
             self._mirror_current = True
             self._mirror_version = self.params._version
         else:
@@ -286,7 +287,17 @@ class HomographyEngine(object):
         b = self.ws[m2.value - base: m2.value - base + n2].reshape(self.B, 1024)
         return a, b
 
+    def materialize_activations(self):
+        """bf16x3 mode keeps activations as 16-bit limb streams; this writes their fp32 values (hi + lo) into the fp32 slots
+        activation() reads.  Returns the size of the leading workspace region whose layout all numeric modes share."""
+        n = ctypes.c_size_t()
+        check(lib.udh_debug_x3_materialize(self._p(self.ws), self.ws_bytes, self.B, self.Pz, ctypes.byref(n), ops._stream()),
+              "udh_debug_x3_materialize")
+        return n.value
+
     def activation(self, layer):
+        if self.numeric == _lib.NUMERIC_BF16X3 and layer < 11:
+            self.materialize_activations()
         ptr, numel = ctypes.c_void_p(), ctypes.c_size_t()
         check(lib.udh_cnn_activation(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, layer, ctypes.byref(ptr),
                                      ctypes.byref(numel)), "udh_cnn_activation")
