@@ -7,7 +7,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_
 from . import build_ext
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libudh.so")
+LIB_PATH = build_ext.lib_path()      # libudh.so (UDH_LIB_VARIANT selects an experimental build variant)
 
 OK, EINVAL, ECUDA, ENOSUP, EWS = 0, -1, -2, -3, -4
 NUMERIC_FP32, NUMERIC_BF16, NUMERIC_BF16X3 = 0, 1, 2
