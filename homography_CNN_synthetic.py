@@ -4,7 +4,8 @@ TestHomography :391-580): same flags, modes, printed metrics and checkpoint cade
 sm_100a CUDA kernels, one process per GPU (torchrun) with one NCCL gradient allreduce per step.
 
 New flags: --synthetic N (generate N pairs on the device instead of reading <data_path>/I, I_prime — MS-COCO is not
-available offline), --seed, --numeric {fp32,bf16}, --num_total_steps (the reference hard-codes 150000, :161).
+available offline), --seed, --numeric {bf16x3,bf16,fp32} (default bf16x3: the parity-certified tensor-core mode),
+--num_total_steps (the reference hard-codes 150000, :161).
 """
 from __future__ import absolute_import, division, print_function
 
@@ -68,7 +69,9 @@ def build_parser():
     # new
     p.add_argument('--synthetic', type=int, default=0, help='generate this many pairs on the device instead of reading data_path')
     p.add_argument('--seed', type=int, default=0)
-    p.add_argument('--numeric', type=str, default='bf16', choices=['fp32', 'bf16'])
+    # bf16x3 = tcgen05 tensor cores with two-limb (fp32-grade) operands: the parity-certified default.  bf16 = single-pass
+    # throughput mode (tenths of a pixel from fp32 on a trained net), fp32 = CUDA cores.
+    p.add_argument('--numeric', type=str, default='bf16x3', choices=['fp32', 'bf16', 'bf16x3'])
     p.add_argument('--num_total_steps', type=int, default=150000)
     return p
 
@@ -257,6 +260,9 @@ def main(argv=None):
         import torch
         n = min(args.num_gpus, torch.cuda.device_count()) if torch.cuda.is_available() else 1
         if n > 1:
+            # build libudh.so once here, before N ranks import the package at the same moment (build_ext also holds a file lock)
+            from unsuperviseddeephomographyral2018_b200 import build_ext
+            build_ext.build()
             # the reference builds num_gpus in-graph towers; here: one process per GPU
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                    "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + (argv if argv is not None else sys.argv[1:])

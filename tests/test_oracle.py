@@ -55,7 +55,7 @@ def test_e2e_golden_regression(golden_dir):
     specs = P.param_specs()
     assert P.num_parameters(specs) == 34192264
     for seed in (0, 1):
-        flat = torch.tensor(P.init_flat(seed))
+        flat = torch.tensor(P.init_flat_large(seed))
         batch = O.make_batch(seed, 2)
         dig = np.array([batch["I_aug"].double().sum().item(), batch["I2_aug"].double().sum().item(),
                         batch["pts1"].double().sum().item(), batch["gt"].double().sum().item()])
@@ -66,6 +66,66 @@ def test_e2e_golden_regression(golden_dir):
             ref = g["s%d_%s" % (seed, k)]
             assert np.allclose(out[k].detach().numpy(), ref, rtol=2e-4, atol=2e-5), k
         assert np.abs(out["pred_I2"].detach().numpy() - g["s%d_pred_I2" % seed]).max() < 1e-3
+        assert np.abs(g["s%d_pred_h4p" % seed]).max() > 10.0              # large-output fixture: pixel tolerances are not vacuous
+        tm = O.test_metrics(out["pred_h4p"].detach(), torch.tensor(g["s%d_gt_metric" % seed]))
+        assert float(tm["num_fail"]) == 0.0
+        assert abs(float(tm["bounded_h_loss"]) - float(g["s%d_bounded_h_loss_m" % seed])) < 1e-4
+
+
+def test_second_restatement_of_rows_C_L_O_agrees_in_fp64():
+    """oracle.py (torch ops) against oracle/numpy_ref.py (plain NumPy loops, written independently from the cited reference
+    lines and the documented TF semantics): regressor forward incl. dropout masks, all six losses, test metrics, and three
+    TF-1 Adam steps, in fp64.  Also pins Adam against a hand-worked vector of the documented ApplyAdam formula."""
+    from oracle import numpy_ref as NR
+    rng = np.random.default_rng(3)
+    Pz, B = 16, 3                                                           # 16x16 patches: conv4 is 2x2x128, fc1 has 512 inputs
+    params = {}
+    for (blk, c, cin, cout) in [(1, 1, 2, 64), (1, 2, 64, 64), (2, 1, 64, 64), (2, 2, 64, 64), (3, 1, 64, 128), (3, 2, 128, 128),
+                                (4, 1, 128, 128), (4, 2, 128, 128)]:
+        s = "model/conv_block%d/conv%d" % (blk, c)
+        params[s + "/weights"] = rng.normal(0, (2.0 / (9 * cin)) ** 0.5, size=(3, 3, cin, cout))
+        params[s + "/biases"] = rng.normal(0, 0.1, size=cout)
+    params["model/fc1/fc1/weights"] = rng.normal(0, 0.05, size=(2 * 2 * 128, 1024)); params["model/fc1/fc1/biases"] = rng.normal(0, 0.1, size=1024)
+    params["model/fc2/fc2/weights"] = rng.normal(0, 0.5, size=(1024, 8)); params["model/fc2/fc2/biases"] = rng.normal(0, 5.0, size=8)
+    x = rng.normal(size=(B, Pz, Pz, 2))
+    keep = (rng.integers(0, 2, size=(B, 2, 2, 128)).astype(np.float64), rng.integers(0, 2, size=(B, 1024)).astype(np.float64))
+    tp = {k: torch.tensor(v) for k, v in params.items()}
+    for km in (None, keep):
+        a = O.vgg_forward(tp, torch.tensor(x), None if km is None else (torch.tensor(km[0]), torch.tensor(km[1]))).numpy()
+        b = NR.vgg_forward(params, x, km)
+        assert np.abs(a).max() > 1.0 and np.abs(a - b).max() <= 1e-11 * np.abs(b).max()
+    pred, gt = rng.normal(0, 20, size=(B, 8)), rng.integers(-45, 46, size=(B, 8)).astype(np.float64)
+    pI, I2 = rng.normal(size=(B, 32, 32, 1)), rng.normal(size=(B, 32, 32, 1))
+    la = O.losses(torch.tensor(pred), torch.tensor(gt), torch.tensor(pI), torch.tensor(I2))
+    lb = NR.losses(pred, gt, pI, I2)
+    for k, v in lb.items():
+        assert abs(float(la[k]) - v) <= 1e-12 * max(1.0, abs(v)), k
+    ta, tb = O.test_metrics(torch.tensor(pred), torch.tensor(gt)), NR.test_metrics(pred, gt)
+    assert np.abs(ta["batch_h_loss"].numpy() - tb["batch_h_loss"]).max() < 1e-12
+    assert float(ta["num_fail"]) == tb["num_fail"] and abs(float(ta["bounded_h_loss"]) - tb["bounded_h_loss"]) < 1e-12
+    # three Adam steps, two restatements
+    p = rng.normal(size=50); m = np.zeros(50); v = np.zeros(50)
+    tp_, tm_, tv_ = torch.tensor(p), torch.zeros(50, dtype=torch.float64), torch.zeros(50, dtype=torch.float64)
+    for t in (1, 2, 3):
+        gr = rng.normal(size=50)
+        p, m, v = NR.adam_tf1(p, gr, m, v, t, 5e-4)
+        tp_, tm_, tv_ = O.adam_step(tp_, torch.tensor(gr), tm_, tv_, t, 5e-4)
+        assert np.abs(tp_.numpy() - p).max() < 1e-15 and np.abs(tv_.numpy() - v).max() < 1e-18
+    # hand-worked: p0 = 1, g = (0.5, -0.25, 1.0), lr = 0.1 (documented ApplyAdam formula, eps outside the bias correction)
+    #   t=1: m = 0.05, v = 2.5e-4, lr_t = 0.1*sqrt(0.001)/0.1            -> p = 1 - 0.0316227766*0.05/(0.0158113883+1e-8)
+    pw, mw, vw = np.array([1.0]), np.zeros(1), np.zeros(1)
+    hand = []
+    for t, gr in ((1, 0.5), (2, -0.25), (3, 1.0)):
+        pw, mw, vw = NR.adam_tf1(pw, np.array([gr]), mw, vw, t, 0.1)
+        hand.append(float(pw[0]))
+    m1, v1 = 0.05, 2.5e-4
+    p1 = 1.0 - (0.1 * np.sqrt(1 - 0.999) / (1 - 0.9)) * m1 / (np.sqrt(v1) + 1e-8)
+    m2, v2 = 0.9 * m1 + 0.1 * -0.25, 0.999 * v1 + 0.001 * 0.0625
+    p2 = p1 - (0.1 * np.sqrt(1 - 0.999 ** 2) / (1 - 0.81)) * m2 / (np.sqrt(v2) + 1e-8)
+    m3, v3 = 0.9 * m2 + 0.1 * 1.0, 0.999 * v2 + 0.001 * 1.0
+    p3 = p2 - (0.1 * np.sqrt(1 - 0.999 ** 3) / (1 - 0.729)) * m3 / (np.sqrt(v3) + 1e-8)
+    assert np.allclose(hand, [p1, p2, p3], rtol=0, atol=1e-15)
+    assert abs(p1 - 0.9000000632) < 1e-9                                    # ~ p0 - lr*sign(g): TF-Adam's first step
 
 
 def test_schedule_and_adam():

@@ -49,7 +49,7 @@ def read_img_and_gt(filenames_file, pts1_file, gt_file):
 
 def _augment(img, rng_gamma, rng_bright, rng_color):
     """dataloader.py:323-375: gamma U(0.8,1.2), brightness U(0.5,2), per-channel colour U(0.8,1.2), clip to [0,255]."""
-    x = (img / 255.0) ** rng_gamma * 255.0
+    x = img ** rng_gamma                       # on the raw 0..255 values, exactly as the reference (img1**random_gamma)
     x = x * rng_bright
     x = x * rng_color.reshape(1, 1, 1, 3)
     return x.clamp(0, 255)

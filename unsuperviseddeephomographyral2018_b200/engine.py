@@ -79,7 +79,11 @@ class HomographyEngine(object):
                         sums=torch.zeros(_lib.NSUMS, device=dev, dtype=torch.float64), photo=torch.zeros(_lib.NLOSSES, device=dev),
                         metrics=torch.zeros(_lib.NMETRICS, device=dev), per=torch.zeros(B, device=dev))
         self._args = _lib.StepArgs()
-        self.dropout_seed = 0x5EED0000 + (seed or 0)
+        # dropout masks are keep_bit(seed + global_step, salt, LOCAL element index): every data-parallel rank needs its own
+        # stream (the reference's towers draw independent masks), parameter init stays rank-independent
+        rank = torch.distributed.get_rank(process_group) if world_size > 1 else 0
+        self.rank = rank
+        self.dropout_seed = (0x5EED0000 + (seed or 0) + rank * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
 
     # ------------------------------------------------------------------ parameters
     def _mirror_is_current(self):
@@ -129,7 +133,7 @@ class HomographyEngine(object):
         st = ops._stream()
         out = OrderedDict()
         h4p = torch.empty(B, 8, device=self.device, dtype=torch.float32)
-        seed = self.dropout_seed + self.global_step if dropout_seed is None else dropout_seed
+        seed = (self.dropout_seed + self.global_step) & 0xFFFFFFFFFFFFFFFF if dropout_seed is None else dropout_seed
         check(lib.udh_cnn_fwd(self._p(self.params), self._p(I1), self._p(I2), self._p(h4p), self._p(self.ws), self.ws_bytes,
                               B, Pz, int(train), seed, self.numeric, st), "udh_cnn_fwd")
         out["pred_h4p"] = h4p
@@ -225,7 +229,7 @@ class HomographyEngine(object):
         a.numeric_mode, a.train = self.numeric, int(train)
         a.fwd_flags = _lib.FWD_FC1_MIRROR_CURRENT if self._mirror_is_current() else 0
         a.loss_type = _lib.STEP_LOSS.get(self.loss_type, -1)
-        a.seed = self.dropout_seed + self.global_step
+        a.seed = (self.dropout_seed + self.global_step) & 0xFFFFFFFFFFFFFFFF
         dp = lambda t: t.data_ptr() if t is not None else None
         a.params, a.grads, a.ws, a.ws_bytes = dp(self.params), dp(self.grads), dp(self.ws), self.ws_bytes
         a.I1, a.I2, a.I_aug, a.pts1, a.gt = dp(batch["I1_aug"]), dp(batch["I2_aug"]), dp(I_aug), dp(batch["pts1"]), dp(batch.get("gt"))
