@@ -1,0 +1,86 @@
+"""GPU tests of the BASELINE.json configurations that had no parity test in round 1:
+  configs[0]  `homography_CNN_synthetic.py --mode test`, batch 4 (the reference's CPU-runnable plumbing case): the printed result
+              table against the oracle's test metrics on the same batches;
+  configs[2]  inference-only CNN + DLT forward at batch 512: sampled rows against the CPU oracle (the oracle cannot run 512
+              samples in seconds; rows are independent, so 8 rows spread over the CTA / tile boundaries pin the batch)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import oracle as O                                               # noqa: E402
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+@pytest.mark.parametrize("numeric", ["bf16x3", "fp32"])
+def test_config2_inference_forward_B512_sampled_rows_vs_oracle(numeric):
+    _need_gpu()
+    from unsuperviseddeephomographyral2018_b200 import engine, params, synthetic, ops
+    B = 512
+    flat = params.init_flat_large(1)
+    eng = engine.HomographyEngine(B, seed=None, numeric=numeric); eng.load_flat(flat)
+    batch = synthetic.make_batch(B, seed=2024)
+    out = eng.eval_step(batch)
+    h = out["pred_h4p"].cpu().double()
+    H = out["H_mat"].cpu().double()
+    rows = [0, 1, 63, 64, 127, 128, 300, 511]
+    p = params.unflatten(torch.tensor(flat), params.param_specs())
+    x = torch.cat([batch["I1_aug"][rows], batch["I2_aug"][rows]], dim=3).cpu()
+    ref = O.vgg_forward(p, x, None).double()
+    scale = ref.abs().max().item()
+    assert scale > 10.0
+    err = (h[rows] - ref).abs().max().item() / scale
+    print("configs[2] B=512 %s: max rel err of pred_h4p on 8 sampled rows %.2e (|pred| up to %.1f px)" % (numeric, err, scale))
+    assert err <= (3e-5 if numeric == "bf16x3" else 1e-5)
+    Href = O.solve_dlt(batch["pts1"][rows].cpu().double(), h[rows])         # DLT of the engine's own prediction, fp64
+    hs = Href.abs().amax(dim=(1, 2), keepdim=True)
+    assert ((H[rows] - Href).abs() / hs).max().item() < 2e-4
+
+
+def test_config0_cli_test_mode_table_vs_oracle(tmp_path):
+    """`--mode test --batch_size 4 --synthetic 16` (3 epochs = 12 iterations): the printed table must equal the oracle's
+    bounded_h_loss / l1_loss / failure rate on the very same batches and weights."""
+    _need_gpu()
+    from unsuperviseddeephomographyral2018_b200 import dataloader as dl, params, synthetic
+    seed, nb, bs = 3, 16, 4
+    model_dir, log_dir, res_dir = str(tmp_path / "m"), str(tmp_path / "l"), str(tmp_path / "r")
+    # a checkpoint with the large-output weights (the CLI restores <model_dir>/<prefix>/<model_name>-<step>.pt)
+    flat = params.init_flat_large(seed)
+    ck_dir = os.path.join(model_dir, "l1_loss_normalize")
+    os.makedirs(ck_dir)
+    z = torch.zeros(len(flat))
+    torch.save(dict(params=torch.tensor(flat), adam_m=z, adam_v=z, global_step=7, patch_size=128), os.path.join(ck_dir, "model.ckpt-7.pt"))
+    cmd = [sys.executable, os.path.join(ROOT, "homography_CNN_synthetic.py"), "--mode", "test", "--batch_size", str(bs), "--synthetic", str(nb),
+           "--num_gpus", "1", "--numeric", "bf16x3", "--seed", str(seed), "--do_augment", "0", "--model_dir", model_dir, "--log_dir", log_dir,
+           "--results_dir", res_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = r.stdout.splitlines()
+    i = next(k for k, ln in enumerate(lines) if ln.startswith("|Steps"))
+    step, h_loss, l1_loss, fail_pct = [float(v) for v in lines[i + 1].split()]
+    assert "no checkpoint" not in r.stdout and int(step) == 3 * (nb // bs) - 1
+    # the same batches through the oracle
+    dparams = dl.dataloader_params(data_path="", filenames_file=None, pts1_file=None, gt_file=None, mode='test', batch_size=bs, img_h=240,
+                                   img_w=320, patch_size=128, augment_list=['normalize'], do_augment=0.0)
+    loader = dl.Dataloader(dparams, shuffle=True, synthetic_pairs=nb, seed=seed * 97 + 12345, device="cuda")
+    p = params.unflatten(torch.tensor(flat), params.param_specs())
+    hs, l1s, fails = [], [], 0.0
+    for _ in range(3 * (nb // bs)):
+        b = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in loader.next_batch().items()}
+        out = O.forward(p, b, None, mode="test")
+        hs.append(float(out["bounded_h_loss"])); l1s.append(float(out["l1_loss"])); fails += float(out["num_fail"])
+    assert abs(h_loss - np.mean(hs)) <= 1e-3, (h_loss, np.mean(hs))
+    assert abs(l1_loss - np.mean(l1s)) <= 2e-4 * np.mean(l1s) + 1e-6, (l1_loss, np.mean(l1s))
+    assert abs(fail_pct - 100.0 * fails / len(hs) / bs) < 1e-9
+    assert re.search(r"Percentile Values", r.stdout)

@@ -74,6 +74,22 @@ def test_data_parallel_contract_gloo_world2(tmp_path):
         gathered = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)
         assert all(torch.equal(gathered[0], x) for x in gathered)
+        # the ENGINE's own two-phase reduction (engine.allreduce_two_phase / dp_slices: head slice, conv backward, conv slice)
+        # on the real flat layout: every element is summed exactly once, the hook between the phases runs, and the per-rank
+        # dropout seeds of the engine differ
+        from unsuperviseddeephomographyral2018_b200 import engine as en, params as P
+        specs = P.param_specs()
+        n = P.total_floats(specs)
+        head, convs = en.dp_slices(specs)
+        cover = torch.zeros(n); cover[head] += 1; cover[convs] += 1
+        assert bool((cover == 1).all()) and head.start == specs["model/fc1/fc1/weights"].offset
+        flat = torch.full((n,), float(rank + 1))
+        flat[specs["model/conv_block1/conv1/weights"].offset] = 10.0 * (rank + 1)
+        seen = []
+        en.allreduce_two_phase(flat, specs, None, between=lambda: seen.append(float(flat[-1])))
+        tot = float(sum(range(1, world + 1)))
+        assert seen == [tot], seen                                     # the head slice was already reduced when the hook ran
+        assert float(flat[1]) == tot and float(flat[-1]) == tot and float(flat[specs["model/conv_block1/conv1/weights"].offset]) == 10.0 * tot
         # per-rank batch sharding as tf.split(batch, num_gpus) (homography_CNN_synthetic.py:199-207)
         full = torch.arange(8)
         assert torch.equal(full.chunk(world)[rank], full[rank * 4:(rank + 1) * 4])

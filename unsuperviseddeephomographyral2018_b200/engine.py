@@ -31,6 +31,25 @@ def learning_rate(step, lr, min_lr, num_total_steps=150000, decay_rate=0.96):
     return lr * decay_rate ** (step // decay_steps(lr, min_lr, num_total_steps, decay_rate))
 
 
+def dp_slices(specs):
+    """Row G (utils/utils.py:380-403) as two slices of the flat gradient buffer: (head, convs).  `head` = fc1 w/b + fc2 w/b
+    (98 % of the bytes, complete after the head phase of the backward, reduced under the conv backward); `convs` = the eight
+    conv layers (complete at the end of the backward).  Together they cover the whole buffer exactly once."""
+    off = specs["model/fc1/fc1/weights"].offset
+    return slice(off, None), slice(0, off)
+
+
+def allreduce_two_phase(flat, specs, group=None, between=None):
+    """sum-allreduce of the flat gradient in the engine's two phases (head slice first, `between()` — the conv backward in
+    the engine — then the conv slice).  Device-agnostic: the gloo CPU test drives exactly this function."""
+    head, convs = dp_slices(specs)
+    torch.distributed.all_reduce(flat[head], group=group)
+    if between is not None:
+        between()
+    torch.distributed.all_reduce(flat[convs], group=group)
+    return flat
+
+
 class HomographyEngine(object):
     def __init__(self, batch_size, patch_size=128, img_h=240, img_w=320, numeric="fp32", seed=0, device=None,
                  lr=1e-4, min_lr=0.9e-4, loss_type="l1_loss", process_group=None, world_size=1):
@@ -186,10 +205,10 @@ class HomographyEngine(object):
         # their allreduce runs on the communication stream underneath the convolution backward.
         cur = torch.cuda.current_stream()
         check(lib.udh_cnn_bwd_phase(*args, _lib.BWD_HEAD, ops._stream()), "udh_cnn_bwd_phase(head)")
-        s16 = self.specs["model/fc1/fc1/weights"]
+        head, _ = dp_slices(self.specs)
         self._comm_stream.wait_stream(cur)
         with torch.cuda.stream(self._comm_stream):
-            torch.distributed.all_reduce(self.grads[s16.offset:], group=self.pg)          # fc1 w, fc1 b, fc2 w, fc2 b
+            torch.distributed.all_reduce(self.grads[head], group=self.pg)                 # fc1 w, fc1 b, fc2 w, fc2 b
         check(lib.udh_cnn_bwd_phase(*args, _lib.BWD_CONVS, ops._stream()), "udh_cnn_bwd_phase(convs)")
         self._head_reduced = True
 
@@ -197,8 +216,8 @@ class HomographyEngine(object):
         """Row G: utils/utils.py:380-403 get_average_grads == allreduce(sum) here, 1/N folded into Adam."""
         if self.world_size > 1:
             if getattr(self, "_head_reduced", False):
-                s16 = self.specs["model/fc1/fc1/weights"]
-                torch.distributed.all_reduce(self.grads[:s16.offset], group=self.pg)      # the 8 conv layers (2.5 MB)
+                _, convs = dp_slices(self.specs)
+                torch.distributed.all_reduce(self.grads[convs], group=self.pg)            # the 8 conv layers (2.5 MB)
                 torch.cuda.current_stream().wait_stream(self._comm_stream)
                 self._head_reduced = False
             else:
@@ -262,12 +281,12 @@ class HomographyEngine(object):
             # Row G with overlap: allreduce the fully connected gradients (134 of 137 MB) under the conv backward
             cur = torch.cuda.current_stream()
             check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_FWD_HEAD, st), "udh_step_forward_backward(head)")
-            s16 = self.specs["model/fc1/fc1/weights"]
+            head, convs = dp_slices(self.specs)
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
-                torch.distributed.all_reduce(self.grads[s16.offset:], group=self.pg)
+                torch.distributed.all_reduce(self.grads[head], group=self.pg)
             check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_CONVS, st), "udh_step_forward_backward(convs)")
-            torch.distributed.all_reduce(self.grads[:s16.offset], group=self.pg)
+            torch.distributed.all_reduce(self.grads[convs], group=self.pg)
             cur.wait_stream(self._comm_stream)
         out = self._step_out(batch)
         out["lr"] = self.update()
