@@ -104,13 +104,12 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
   } else if (warp == 0) {
     // ===================================== weight-ring producer =====================================
     if (lane == 0) {
-      uint32_t wcount = 0;
+      uint32_t ws = 0, wpar = 1;                                  // first pass over the ring: the slots are free
       auto push = [&](int block) {
-        const int s = wcount % stages;
-        mbar_wait(&w_empty[s], ((wcount / stages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&w_full[s], N_OUT * 128);
-        tma_load_2d(sW + (size_t)s * N_OUT * 128, &tmW, 0, block * N_OUT, &w_full[s]);
-        ++wcount;
+        mbar_wait(&w_empty[ws], wpar);
+        mbar_arrive_expect_tx(&w_full[ws], N_OUT * 128);
+        tma_load_2d(sW + (size_t)ws * N_OUT * 128, &tmW, 0, block * N_OUT, &w_full[ws]);
+        if (++ws == (uint32_t)stages) { ws = 0; wpar ^= 1u; }
       };
       for (int it = 0; it < my_items; ++it) {
         for (int kb = 0; kb < 9 * CB; ++kb) push(kb * 2);                       // phase LO: A_lo x W_hi
@@ -122,7 +121,11 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     // The whole warp stays converged (descriptors live in uniform registers); one elected lane issues.
     constexpr uint32_t idesc = make_idesc_f16kind(128, N_OUT, 0, 0, FMT_A, FMT_W);
     const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
-    uint32_t wcount = 0;
+    // ring position as a running (stage, parity) pair and taps as running (ky, kx) counters: the issue loop of this single
+    // warp is the serial resource of the kernel, so it carries no integer division and no per-block address rebuild
+    uint32_t ws = 0, wpar = 0;
+    const uint32_t w_stage_units = (uint32_t)(N_OUT * 128) >> 4;
+    const uint32_t w_lo0 = desc_lo(w_addr0, 16);
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
       mbar_wait(&t_empty[b], ((it >> 1) & 1) ^ 1);
@@ -132,31 +135,40 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
         const int l = 1 - ph;                                     // phase 0 consumes the lo limb, phase 1 the hi limb
         mbar_wait(&a_full[l], it & 1);
         tc_fence_after();
-        const int nblk = ph == 0 ? 9 * CB : 18 * CB;
+        // descriptor (low word) of tap (0,0), channel block 0 of this limb: rows start at hh - Wp - 1
+        const uint32_t a_tap0 = desc_lo(a_addr0 + (uint32_t)(l * CB) * abuf_bytes + (uint32_t)(g.hh - g.Wp - 1) * 128, 16);
+        const uint32_t cb_units = (uint32_t)abuf_bytes >> 4;
+        uint32_t first = ph == 0 ? 0u : 1u;                       // the very first MMA of the item overwrites the accumulators
 #pragma unroll 1
-        for (int j = 0; j < nblk; ++j) {
-          const int kb = ph == 0 ? j : (j >> 1);
-          const int tap = kb / CB, cb = kb - tap * CB;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          const int off = (ky - 1) * g.Wp + (kx - 1);
-          const int s = wcount % stages;
-          mbar_wait(&w_full[s], (wcount / stages) & 1);
-          tc_fence_after();
-          const uint32_t a_lo = desc_lo(a_addr0 + (uint32_t)(l * CB + cb) * abuf_bytes + (uint32_t)(g.hh + off) * 128, 16);
-          const uint32_t w_lo = desc_lo(w_addr0 + (uint32_t)s * N_OUT * 128, 16);
-          const uint32_t first = (ph == 0 && j == 0) ? 0u : 1u;
-          if (elect_one()) {
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll 1
+          for (int kx = 0; kx < 3; ++kx) {
+            const uint32_t a_tap = a_tap0 + (uint32_t)(ky * g.Wp + kx) * 8;      // 128-byte rows = 8 sixteen-byte units
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
+            for (int cb = 0; cb < CB; ++cb) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)     // +1024 sixteen-byte units per tile, +2 per 32-byte k-step
-                umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
-                          (first | (uint32_t)(k > 0)) ? 1u : 0u);
+              for (int wl = 0; wl < 2; ++wl) {
+                if (wl == 1 && ph == 0) continue;                 // phase LO multiplies with W_hi only
+                mbar_wait(&w_full[ws], wpar);
+                tc_fence_after();
+                const uint32_t a_lo = a_tap + (uint32_t)cb * cb_units;
+                const uint32_t w_lo = w_lo0 + ws * w_stage_units;
+                if (elect_one()) {
+#pragma unroll
+                  for (int t = 0; t < T; ++t) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)     // +1024 sixteen-byte units per tile, +2 per 32-byte k-step
+                      umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
+                                (first | (uint32_t)(k > 0)) ? 1u : 0u);
+                  }
+                  umma_commit(&w_empty[ws]);
+                }
+                __syncwarp();
+                first = 1u;
+                if (++ws == (uint32_t)stages) { ws = 0; wpar ^= 1u; }
+              }
             }
-            umma_commit(&w_empty[s]);
           }
-          __syncwarp();
-          ++wcount;
         }
         if (elect_one()) {
           umma_commit(&a_empty[l]);                               // this limb's rows are no longer read -> producer
