@@ -417,7 +417,7 @@ def other_configs(torch, _lib, engine, synthetic, numeric, peaks, dev):
         _lib.check(_lib.lib.udh_dlt_fwd(p(pts), p(hh), p(Hm), B4, st), "dlt")
 
         def warp(i):
-            _lib.check(_lib.lib.udh_warp_loss_fwd(p(src[i % nb]), 1, Hh, W, p(Hm), p(tgt[i % nb]), None, 0, W, Hh, None, p(sums), B4, st), "warp")
+            _lib.check(_lib.lib.udh_warp_loss_fwd_ex(p(src[i % nb]), 1, Hh, W, p(Hm), p(tgt[i % nb]), None, 0, W, Hh, None, p(sums), 0, B4, st), "warp")
         for i in range(4):
             warp(i)
         e0, e1 = ev(), ev(); torch.cuda.synchronize(); e0.record()

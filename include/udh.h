@@ -95,6 +95,10 @@ int udh_dlt_bwd(const float* pts1, const float* h4p, const float* H, const float
 int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
                       const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, float* pred, double* sums,
                       int B, void* stream);
+/* all_sums = 0: accumulate sums[UDH_SUM_ABS] only (what l1_loss needs) — the variant BASELINE configs[3] measures. */
+int udh_warp_loss_fwd_ex(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                         const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, float* pred, double* sums,
+                         int all_sums, int B, void* stream);
 /* d loss / d H [B,9] for loss_type in UDH_LOSS_*; `sums` is the forward accumulator (needed by REC),
  * upstream multiplies the gradient (1.0 for a plain backward).  Recomputes the warp; no image-sized
  * intermediates.  scratch: float[B*9], caller-provided. */
@@ -222,6 +226,24 @@ int udh_step_forward_backward(const udh_step_args* args, int phase, void* stream
  * (x0,y0) = pts1[0:2], and patch_origin[B] = y0*img_w + x0 (the first patch index of each sample). */
 int udh_prep_inputs_u8(const uint8_t* I, const uint8_t* I_prime, const float* pts1, float* I_aug, float* I1, float* I2,
                        int32_t* patch_origin, int B, int img_h, int img_w, int P, void* stream);
+
+/* Same pipeline with the reference's photometric augmentation (dataloader.py:163-169,323-375) fused in, and a GRAY warp
+ * source: aug (nullable) = [B,11] {on, gamma, brightness, colour R/G/B for I, then the same five for I'} — joint
+ * augmentation (train) passes the same five numbers twice, disjoint (test) two draws; gamma acts on the raw 0..255 values.
+ * Outputs: I_gray [B,img_h,img_w] = channel mean of the normalised (augmented) I — the warp's channel mean commutes with
+ * its linear sampling, so the warp kernel can read this plane with C = 1 (a third of the bytes); I_aug3 (nullable) the
+ * 3-channel tensor of the reference contract; I1_aug, I2_aug [B,P,P] the CNN input / L1 target; I1, I2 (nullable, together)
+ * the un-augmented patches (summaries only in the reference); patch_origin [B] (nullable). */
+int udh_prep_inputs_u8_ex(const uint8_t* I, const uint8_t* I_prime, const float* pts1, const float* aug, float* I_gray, float* I_aug3,
+                          float* I1, float* I2, float* I1_aug, float* I2_aug, int32_t* patch_origin, int B, int img_h, int img_w,
+                          int P, void* stream);
+/* ---- on-device synthetic pairs (utils/gen_synthetic_data.py:40-68; MS-COCO is not available offline) ---------------
+ * udh_synth_scene_u8: seeded multi-octave texture I [B,img_h,img_w,3] uint8, patch corners pts1 [B,8] with
+ * x0 in [rho, W-rho-P], y0 in [rho, Hh-rho-P] (:42-50) and integer corner perturbations gt [B,8] in [-rho, rho] (:53).
+ * udh_dlt_fwd(pts1, gt) then gives H_gt (:56) and udh_warp_image_u8 the second image I' = uint8(warp(I, H_gt)) (:63-64,
+ * numpy_spatial_transformer.py:131-146). */
+int udh_synth_scene_u8(uint8_t* I, float* pts1, float* gt, int B, int img_h, int img_w, int P, int rho, uint64_t seed, void* stream);
+int udh_warp_image_u8(const uint8_t* U, const float* H, uint8_t* out, int B, int img_h, int img_w, void* stream);
 
 /* ---- instrumentation read by bench.py -------------------------------------------------------------------------
  * udh_launch_count: kernels this library has launched in this process (monotonic).

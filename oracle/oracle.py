@@ -379,3 +379,39 @@ def make_batch(seed, B, img_h=240, img_w=320, patch=128, rho=45, dtype=torch.flo
     return OrderedDict(I1=t(I1), I2=t(I2), I1_aug=t(I1), I2_aug=t(I2), I_aug=t(I_n), I_prime_aug=t(Ip_n),
                        pts1=t(pts1), gt=t(gt), patch_indices=torch.tensor(idx), I_u8=I_u8, I_prime_u8=Ip_u8,
                        H_gt=H_gt)
+
+
+# ----------------------------------------------------------------------------------------------
+# Input pipeline after JPEG decode (code/dataloader.py:163-177,203-227,323-375)
+# ----------------------------------------------------------------------------------------------
+
+def augment_image(img, gamma, brightness, colors, min_val=0.0, max_val=255.0):
+    """One image of joint_/disjoint_augment_image_pair (:323-375): img ** gamma on the RAW 0..255 float values, then
+    brightness, then the per-channel colour image, then clip_by_value."""
+    x = img ** gamma
+    x = x * brightness
+    x = x * colors.reshape(1, 1, 3)
+    return x.clamp(min_val, max_val)
+
+
+def prep_inputs(I_u8, Ip_u8, pts1, aug=None, patch=128):
+    """Post-dataloader tensors from decoded uint8 images (fp32, as the reference): optional augmentation (aug [B,11] =
+    {on, gamma, brightness, colour RGB of I, the same five of I'}), normalisation of BOTH images with I's statistics
+    (:173-177), gray = channel mean, patch gather at (x0, y0) = pts1[0:2] (:203-227)."""
+    I = torch.as_tensor(I_u8).to(torch.float32); Ip = torch.as_tensor(Ip_u8).to(torch.float32)
+    B, Hh, W, _ = I.shape
+    mean, std = torch.tensor(MEAN_I), torch.tensor(STD_I)
+    Ia, Ipa = I.clone(), Ip.clone()
+    if aug is not None:
+        for b in range(B):
+            if float(aug[b, 0]) != 0.0:
+                Ia[b] = augment_image(I[b], aug[b, 1], aug[b, 2], aug[b, 3:6])
+                Ipa[b] = augment_image(Ip[b], aug[b, 6], aug[b, 7], aug[b, 8:11])
+    norm = lambda t: (t - mean) / std
+    I_n, Ip_n, Ia_n, Ipa_n = norm(I), norm(Ip), norm(Ia), norm(Ipa)
+    x0 = pts1[:, 0].long(); y0 = pts1[:, 1].long()
+    yy, xx = torch.meshgrid(torch.arange(patch), torch.arange(patch), indexing="ij")
+    idx = ((yy[None] + y0[:, None, None]) * W + (xx[None] + x0[:, None, None])).reshape(B, -1)
+    g = lambda t: torch.gather(t.mean(dim=3).reshape(B, -1), 1, idx).reshape(B, patch, patch, 1)
+    return OrderedDict(I1=g(I_n), I2=g(Ip_n), I1_aug=g(Ia_n), I2_aug=g(Ipa_n), I_aug=Ia_n, I_prime_aug=Ipa_n,
+                       patch_indices=idx.to(torch.int32))

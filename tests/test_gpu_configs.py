@@ -78,9 +78,55 @@ def test_config0_cli_test_mode_table_vs_oracle(tmp_path):
     hs, l1s, fails = [], [], 0.0
     for _ in range(3 * (nb // bs)):
         b = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in loader.next_batch().items()}
+        # the fast generator hands over the window ORIGIN of each sample; the oracle gathers with the full index table
+        x0 = b["pts1"][:, 0].long(); y0 = b["pts1"][:, 1].long()
+        yy, xx = torch.meshgrid(torch.arange(128), torch.arange(128), indexing="ij")
+        b["patch_indices"] = ((yy[None] + y0[:, None, None]) * 320 + (xx[None] + x0[:, None, None])).reshape(bs, -1).to(torch.int32)
         out = O.forward(p, b, None, mode="test")
         hs.append(float(out["bounded_h_loss"])); l1s.append(float(out["l1_loss"])); fails += float(out["num_fail"])
     assert abs(h_loss - np.mean(hs)) <= 1e-3, (h_loss, np.mean(hs))
     assert abs(l1_loss - np.mean(l1s)) <= 2e-4 * np.mean(l1s) + 1e-6, (l1_loss, np.mean(l1s))
     assert abs(fail_pct - 100.0 * fails / len(hs) / bs) < 1e-9
     assert re.search(r"Percentile Values", r.stdout)
+
+
+def test_fused_prep_kernel_augmentation_vs_oracle():
+    """udh_prep_inputs_u8_ex (augment on the raw 0..255 values + normalise + gray + patch gather, one kernel) against the
+    oracle's restatement of code/dataloader.py:163-177,203-227,323-375, joint and disjoint parameter tables; and the fast
+    on-device generator's pairs are self-consistent (warp with H_gt reproduces I2 up to the uint8 cast)."""
+    _need_gpu()
+    from unsuperviseddeephomographyral2018_b200 import synthetic, ops
+    B = 5
+    sb = synthetic.make_batch_fast(B, seed=11)
+    assert sb["pts1"][:, 0].min() >= 45 and sb["pts1"][:, 0].max() <= 147 and sb["pts1"][:, 1].min() >= 45 and sb["pts1"][:, 1].max() <= 67
+    assert sb["gt"].abs().max() <= 45 and torch.equal(sb["gt"], sb["gt"].round()) and sb["gt"].abs().max() >= 30
+    assert sb["I_u8"].float().std() > 20 and sb["I_u8"].float().mean() > 80 and sb["I_u8"].float().mean() < 175
+    # the second image is the reference's generator step: uint8(transformer(I, M^-1 H_gt M)) (gen_synthetic_data.py:56-64)
+    Hgt = ops.dlt_forward(sb["pts1"], sb["gt"])
+    M = torch.tensor([[160.0, 0., 160.0], [0., 120.0, 120.0], [0., 0., 1.]], device="cuda")
+    theta = (torch.linalg.inv(M) @ Hgt @ M).contiguous()
+    Ip_ref, _ = ops.transformer(sb["I_u8"].float().contiguous(), theta, (240, 320))
+    dI = (sb["I_prime_u8"].int() - Ip_ref.clamp(0, 255).to(torch.uint8).int()).abs()
+    assert (dI > 1).float().mean().item() < 1e-3 and dI.float().mean().item() < 0.05     # theta is rounded differently: isolated +-1 levels
+    # self-consistency: warping I with H_gt reproduces the I2 patch up to the uint8 truncation of I' (< 1.5 grey levels)
+    _, sums = ops.warp_loss_forward(sb["I_aug"], Hgt, sb["I2_aug"], sb["patch_indices"], 128, 128, want_pred=False)
+    print("mean |warp(I, H_gt) - I2| = %.4f normalised units" % (sums[0].item() / (B * 128 * 128)))
+    assert sums[0].item() / (B * 128 * 128) < 1.5 / 69.0
+    rng = np.random.default_rng(5)
+    for joint in (True, False):
+        aug = np.zeros((B, 11), np.float32)
+        aug[:, 0] = [1, 0, 1, 1, 1]
+        a = np.concatenate([rng.uniform(0.8, 1.2, (B, 1)), rng.uniform(0.5, 2.0, (B, 1)), rng.uniform(0.8, 1.2, (B, 3))], 1)
+        b = a if joint else np.concatenate([rng.uniform(0.8, 1.2, (B, 1)), rng.uniform(0.5, 2.0, (B, 1)), rng.uniform(0.8, 1.2, (B, 3))], 1)
+        aug[:, 1:6], aug[:, 6:11] = a, b
+        got = synthetic.prep_u8(sb["I_u8"], sb["I_prime_u8"], sb["pts1"], torch.tensor(aug).cuda(), 128, want_rgb=True)
+        ref = O.prep_inputs(sb["I_u8"].cpu(), sb["I_prime_u8"].cpu(), sb["pts1"].cpu(), torch.tensor(aug), 128)
+        assert (got["I_aug_rgb"].cpu() - ref["I_aug"]).abs().max() <= 2e-4          # powf vs torch.pow: a few ulp of 255^1.2
+        assert (got["I_aug"].cpu()[..., 0] - ref["I_aug"].mean(dim=3)).abs().max() <= 2e-4
+        for k in ("I1", "I2", "I1_aug", "I2_aug"):
+            assert (got[k].cpu() - ref[k]).abs().max() <= 2e-4, k
+        assert torch.equal(got["patch_indices"].cpu(), ref["patch_indices"][:, 0])
+        # sample 1 is not augmented: identical to the plain path, bit for bit
+        assert torch.equal(got["I1_aug"][1], got["I1"][1]) and torch.equal(got["I2_aug"][1], got["I2"][1])
+        # an augmented sample really changed, and saturates like the reference (x ** gamma on 0..255 clips at 255)
+        assert (got["I1_aug"][0] - got["I1"][0]).abs().max() > 0.05

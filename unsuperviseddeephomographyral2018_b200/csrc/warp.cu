@@ -128,8 +128,12 @@ __device__ __forceinline__ float sample_pixel(const float* __restrict__ img, con
   const float xs = fmaf(hm.h[0], xt, bx), ys = fmaf(hm.h[3], xt, by);
   float ts = fmaf(hm.h[6], xt, bt);
   if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;
-  const float x = (xs / ts + 1.0f) * (float)W / 2.0f;
-  const float y = (ys / ts + 1.0f) * (float)Hh / 2.0f;
+  // ONE correctly rounded reciprocal instead of two IEEE divisions (the kernel is issue-bound, not DRAM-bound: ncu of round 1):
+  // xs * (1/ts) is within 1.5 ulp of xs / ts, i.e. < 5e-5 px on coordinates of a few hundred px — far inside the parity
+  // tolerance of the warp (2e-4 on 99.9 % of the pixels).  Samples that clip take the reference-exact path below.
+  const float rt = __frcp_rn(ts);
+  const float x = (xs * rt + 1.0f) * (float)W * 0.5f;
+  const float y = (ys * rt + 1.0f) * (float)Hh * 0.5f;
   if (x >= 0.0f && x < (float)(W - 1) && y >= 0.0f && y < (float)(Hh - 1)) {
     // no tap clips: floor == truncation, x1 = x0 + 1 — same fp32 values as the general path
     const int x0 = (int)x, y0 = (int)y;
@@ -151,7 +155,8 @@ __device__ __forceinline__ float sample_pixel(const float* __restrict__ img, con
   return sample_gray<C>(img, t);
 }
 
-template <int C>
+// ALL = true: the six reductions every photometric diagnostic needs; false: sum |pred - I2| only (l1_loss)
+template <int C, bool ALL>
 __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restrict__ I, int img_h, int img_w,
                                                             const float* __restrict__ H, const float* __restrict__ I2,
                                                             const int32_t* __restrict__ patch_indices, int64_t idx_stride,
@@ -195,22 +200,30 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
           for (int k = 0; k < 4; ++k) {
             const float d = p[k] - tg[k], ad = fabsf(d);
             s_abs += ad;
-            s_sq = fmaf(d, d, s_sq);
-            s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-            s_xy = fmaf(p[k], tg[k], s_xy);
-            s_xx = fmaf(p[k], p[k], s_xx);
-            s_yy = fmaf(tg[k], tg[k], s_yy);
+            if (ALL) {
+              s_sq = fmaf(d, d, s_sq);
+              s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+              s_xy = fmaf(p[k], tg[k], s_xy);
+              s_xx = fmaf(p[k], p[k], s_xx);
+              s_yy = fmaf(tg[k], tg[k], s_yy);
+            }
           }
         }
       }
     }
   }
   if (sums && I2) {
-    double acc[6] = {s_abs, s_sq, s_hub, s_xy, s_xx, s_yy};
-    block_sum<double, 6>(acc, red);
-    if (threadIdx.x == 0) {
+    if (ALL) {
+      double acc[6] = {s_abs, s_sq, s_hub, s_xy, s_xx, s_yy};
+      block_sum<double, 6>(acc, red);
+      if (threadIdx.x == 0) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) atomicAdd(sums + i, acc[i]);
+        for (int i = 0; i < 6; ++i) atomicAdd(sums + i, acc[i]);
+      }
+    } else {
+      double acc[1] = {s_abs};
+      block_sum<double, 1>(acc, red);
+      if (threadIdx.x == 0) atomicAdd(sums + UDH_SUM_ABS, acc[0]);
     }
   }
 }
@@ -424,9 +437,46 @@ __global__ void __launch_bounds__(256) transformer_kernel(const float* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// synthetic-pair generation (code/utils/gen_synthetic_data.py:56-64): I' = warp of the uint8 image I with the pixel-unit
+// homography H (theta = M^-1 H M, numpy_spatial_transformer.py:135-146), cast back to uint8 (:131).  Same sampling code as
+// the training-time warp above, uint8 in / uint8 out, all 3 channels of a pixel per thread.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) warp_image_u8_kernel(const uint8_t* __restrict__ U, const float* __restrict__ H,
+                                                            uint8_t* __restrict__ out, int Hh, int W) {
+  const int b = blockIdx.y;
+  Homog hm;
+  normalise_h(H + (size_t)b * 9, W, Hh, hm);
+  hm.step_x = 2.0f / (float)(W - 1);
+  hm.step_y = 2.0f / (float)(Hh - 1);
+  const uint8_t* img = U + (size_t)b * Hh * W * 3;
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < Hh * W; o += gridDim.x * blockDim.x) {
+    const int r = o / W, c = o - r * W;
+    Tap t;
+    sample_setup(hm, fmaf(hm.step_x, (float)c, -1.0f), fmaf(hm.step_y, (float)r, -1.0f), W, Hh, t);
+    uint8_t* dst = out + ((size_t)b * Hh * W + o) * 3;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float Ia = (float)__ldg(img + (size_t)t.i00 * 3 + ch), Ib = (float)__ldg(img + (size_t)t.i10 * 3 + ch);
+      const float Ic = (float)__ldg(img + (size_t)t.i01 * 3 + ch), Id = (float)__ldg(img + (size_t)t.i11 * 3 + ch);
+      const float v = bilinear_rn(t, Ia, Ib, Ic, Id);
+      dst[ch] = (uint8_t)fminf(fmaxf(v, 0.0f), 255.0f);       // clamp, then truncate like astype(uint8)
+    }
+  }
+}
+
 }  // namespace udh
 
 using namespace udh;
+
+extern "C" int udh_warp_image_u8(const uint8_t* U, const float* H, uint8_t* out, int B, int img_h, int img_w, void* stream) {
+  UDH_REQUIRE(U && H && out, "udh_warp_image_u8: null pointer");
+  UDH_REQUIRE(B >= 0 && img_h >= 2 && img_w >= 2, "udh_warp_image_u8: bad dimensions");
+  if (B == 0) return UDH_OK;
+  dim3 grid(min((img_h * img_w + 255) / 256, 1024), B);
+  warp_image_u8_kernel<<<grid, 256, 0, as_stream(stream)>>>(U, H, out, img_h, img_w);
+  return check_launch("udh_warp_image_u8");
+}
 
 static int check_warp_args(const char* fn, const float* I, int C, int img_h, int img_w, const float* H, int pw, int ph,
                            int B) {
@@ -440,16 +490,26 @@ static int check_warp_args(const char* fn, const float* I, int C, int img_h, int
 extern "C" int udh_warp_loss_fwd(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
                                  const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, float* pred,
                                  double* sums, int B, void* stream) {
+  return udh_warp_loss_fwd_ex(I, C, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums, 1, B, stream);
+}
+
+extern "C" int udh_warp_loss_fwd_ex(const float* I, int C, int img_h, int img_w, const float* H, const float* I2,
+                                    const int32_t* patch_indices, int64_t idx_stride, int pw, int ph, float* pred,
+                                    double* sums, int all_sums, int B, void* stream) {
   int rc = check_warp_args("udh_warp_loss_fwd", I, C, img_h, img_w, H, pw, ph, B);
   if (rc) return rc;
   UDH_REQUIRE(pred || (I2 && sums), "udh_warp_loss_fwd: nothing to compute (no pred, no I2+sums)");
   if (B == 0) return UDH_OK;
   dim3 grid(((pw + 127) / 128) * ((ph + 31) / 32), B);
   ProfScope ps(PROF_WARP_FWD, as_stream(stream));
-  if (C == 3)
-    launch_chain(warp_loss_fwd_kernel<3>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+  if (C == 3 && all_sums)
+    launch_chain(warp_loss_fwd_kernel<3, true>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+  else if (C == 3)
+    launch_chain(warp_loss_fwd_kernel<3, false>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+  else if (all_sums)
+    launch_chain(warp_loss_fwd_kernel<1, true>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
   else
-    launch_chain(warp_loss_fwd_kernel<1>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
+    launch_chain(warp_loss_fwd_kernel<1, false>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
   return check_launch("udh_warp_loss_fwd");
 }
 

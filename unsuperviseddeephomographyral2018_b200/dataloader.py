@@ -47,14 +47,6 @@ def read_img_and_gt(filenames_file, pts1_file, gt_file):
     return names, pts1, gt
 
 
-def _augment(img, rng_gamma, rng_bright, rng_color):
-    """dataloader.py:323-375: gamma U(0.8,1.2), brightness U(0.5,2), per-channel colour U(0.8,1.2), clip to [0,255]."""
-    x = img ** rng_gamma                       # on the raw 0..255 values, exactly as the reference (img1**random_gamma)
-    x = x * rng_bright
-    x = x * rng_color.reshape(1, 1, 1, 3)
-    return x.clamp(0, 255)
-
-
 class Dataloader(object):
     def __init__(self, params, shuffle=True, synthetic_pairs=0, seed=0, device="cuda", rho=45):
         self.params = params
@@ -107,33 +99,33 @@ class Dataloader(object):
         for j, i in enumerate(idx):
             I[j], Ip[j] = self._read_pair(i)
         dev = self.device
-        I_f = torch.from_numpy(I).to(dev).float(); Ip_f = torch.from_numpy(Ip).to(dev).float()
-        I_aug, Ip_aug = I_f.clone(), Ip_f.clone()
-        do = self._rng.uniform(0, 1, size=B) > (1 - p.do_augment)                                  # dataloader.py:163-169
-        for j in np.nonzero(do)[0]:
-            g, b, c = self._rng.uniform(0.8, 1.2), self._rng.uniform(0.5, 2.0), self._rng.uniform(0.8, 1.2, size=3)
-            I_aug[j:j + 1] = _augment(I_f[j:j + 1], g, b, torch.tensor(c, device=dev, dtype=torch.float32))
-            if self.mode != 'train':                                                               # disjoint noise in test
-                g, b, c = self._rng.uniform(0.8, 1.2), self._rng.uniform(0.5, 2.0), self._rng.uniform(0.8, 1.2, size=3)
-            Ip_aug[j:j + 1] = _augment(Ip_f[j:j + 1], g, b, torch.tensor(c, device=dev, dtype=torch.float32))
-        if 'normalize' in p.augment_list:                                                          # dataloader.py:172-177
-            mean = torch.tensor(synthetic.MEAN_I, device=dev); std = torch.tensor(synthetic.STD_I, device=dev)
-            I_f, Ip_f, I_aug, Ip_aug = [((t - mean) / std).contiguous() for t in (I_f, Ip_f, I_aug, Ip_aug)]
+        I_u8 = torch.from_numpy(I).to(dev); Ip_u8 = torch.from_numpy(Ip).to(dev)
+        if 'normalize' not in p.augment_list:
+            raise NotImplementedError("augment_list without 'normalize' is not supported (the reference default is ['normalize'])")
+        # augmentation parameters on the host RNG (reproducible order), applied by the fused device kernel
+        aug = np.zeros((B, 11), np.float32)
+        aug[:, 0] = self._rng.uniform(0, 1, size=B) > (1 - p.do_augment)                          # dataloader.py:163-169
+        draw = lambda: np.concatenate([[self._rng.uniform(0.8, 1.2), self._rng.uniform(0.5, 2.0)], self._rng.uniform(0.8, 1.2, size=3)])
+        for j in range(B):
+            a = draw()
+            aug[j, 1:6] = a
+            aug[j, 6:11] = a if self.mode == 'train' else draw()                                   # joint (train) / disjoint (test)
         pts1 = torch.tensor(self.pts1[idx], dtype=torch.float32, device=dev)
         gt = torch.tensor(self.gt[idx], dtype=torch.float32, device=dev) if self.gt is not None else None
-        x0 = pts1[:, 0].long(); y0 = pts1[:, 1].long()
-        yy, xx = torch.meshgrid(torch.arange(P, device=dev), torch.arange(P, device=dev), indexing="ij")
-        pidx = ((yy[None] + y0[:, None, None]) * W + (xx[None] + x0[:, None, None])).reshape(B, -1)   # dataloader.py:203-207
-        g = lambda t: torch.gather(t.mean(dim=3).reshape(B, -1), 1, pidx).reshape(B, P, P, 1).contiguous()
-        return dict(I1=g(I_f), I2=g(Ip_f), I1_aug=g(I_aug), I2_aug=g(Ip_aug), I_aug=I_aug.contiguous(), I_prime_aug=Ip_aug.contiguous(),
-                    pts1=pts1, gt=gt, patch_indices=pidx.to(torch.int32).contiguous())
+        out = synthetic.prep_u8(I_u8, Ip_u8, pts1, torch.tensor(aug, device=dev), P, want_rgb=True)
+        out["gt"] = gt
+        out["I_aug"] = out.pop("I_aug_rgb")                        # the reference contract: [B,Hh,W,3] normalised (augmented) I
+        return out
 
     # ---- public ---------------------------------------------------------------------------------------------------
     def next_batch(self):
         p = self.params
         if self.synthetic_pairs:
-            b = synthetic.make_batch(p.batch_size, seed=self.seed * 1000003 + self._step, img_h=p.img_h, img_w=p.img_w,
-                                     patch=p.patch_size, rho=self.rho, device=self.device)
+            # on-device generator + fused augment / normalise / gray / crop (four kernel launches per batch); photometric
+            # augmentation as the reference: probability do_augment, joint in train, disjoint in test
+            b = synthetic.make_batch_fast(p.batch_size, seed=self.seed * 1000003 + self._step, img_h=p.img_h, img_w=p.img_w,
+                                          patch=p.patch_size, rho=self.rho, device=self.device, do_augment=float(p.do_augment),
+                                          mode=self.mode)
         else:
             b = self._disk_batch()
         self._step += 1

@@ -7,10 +7,13 @@ reference's spatial-transformer convention, uint8 cast — and the dataloader's 
 gather by patch_indices).  MS-COCO is not available offline, so I is a seeded band-limited random texture.
 The homography and the warp run through libudh (udh_dlt_fwd, udh_transformer_fwd); torch only moves bytes.
 """
+import ctypes
+
 import torch
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import check, lib
 
 MEAN_I = (118.93, 113.97, 102.60)
 STD_I = (69.85, 68.81, 72.45)
@@ -62,3 +65,62 @@ def make_batch(B, seed=0, img_h=240, img_w=320, patch=128, rho=45, device="cuda"
     I2 = torch.gather(gray_Ip, 1, idx).reshape(B, patch, patch, 1).contiguous()
     return dict(I1=I1, I2=I2, I1_aug=I1, I2_aug=I2, I_aug=I_n, I_prime_aug=Ip_n, pts1=pts1, gt=gt,
                 patch_indices=idx.to(torch.int32).contiguous(), I_u8=I_u8, I_prime_u8=Ip_u8)
+
+
+def draw_augmentation(B, do_augment, mode, generator, device):
+    """Per-sample parameters of the reference's photometric augmentation (code/dataloader.py:163-169,323-375) as the
+    [B,11] table udh_prep_inputs_u8_ex takes: {on, gamma, brightness, colour RGB for I, then the same five for I'}.
+    A sample is augmented when u > 1 - do_augment (:167,169); train = JOINT (one draw for the pair), test = DISJOINT."""
+    u = torch.rand(B, device=device, generator=generator)
+    def five():
+        g = torch.rand(B, 5, device=device, generator=generator)
+        lo = torch.tensor([0.8, 0.5, 0.8, 0.8, 0.8], device=device); hi = torch.tensor([1.2, 2.0, 1.2, 1.2, 1.2], device=device)
+        return lo + g * (hi - lo)
+    a = five()
+    b = a if mode == 'train' else five()
+    return torch.cat([(u > (1.0 - do_augment)).float().unsqueeze(1), a, b], dim=1).contiguous()
+
+
+def make_batch_fast(B, seed=0, img_h=240, img_w=320, patch=128, rho=45, device="cuda", do_augment=0.0, mode='train', want_rgb=False):
+    """The same post-dataloader tensors as make_batch, produced by four kernel launches (udh_synth_scene_u8, udh_dlt_fwd,
+    udh_warp_image_u8, udh_prep_inputs_u8_ex) instead of ~40 eager torch ops, with the reference's photometric augmentation
+    (joint in train, disjoint in test) applied on the device when do_augment > 0.  `I_aug` is the GRAY warp source
+    [B,Hh,W,1] (the channel mean commutes with the warp's linear sampling); want_rgb=True also returns the 3-channel tensor
+    of the reference contract as `I_aug_rgb`.  `patch_indices` holds the window origin of each sample ([B] int32): the
+    kernels only ever read the first gathered index (dataloader.py:203-207)."""
+    dev = torch.device(device)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = ops._stream()
+    I_u8 = torch.empty(B, img_h, img_w, 3, device=dev, dtype=torch.uint8)
+    Ip_u8 = torch.empty_like(I_u8)
+    pts1 = torch.empty(B, 8, device=dev); gt = torch.empty(B, 8, device=dev)
+    check(lib.udh_synth_scene_u8(p(I_u8), p(pts1), p(gt), B, img_h, img_w, patch, rho, int(seed) & 0xFFFFFFFFFFFFFFFF, st), "udh_synth_scene_u8")
+    H_gt = ops.dlt_forward(pts1, gt)
+    check(lib.udh_warp_image_u8(p(I_u8), p(H_gt), p(Ip_u8), B, img_h, img_w, st), "udh_warp_image_u8")
+    aug = None
+    if do_augment > 0:
+        gen = torch.Generator(device=dev); gen.manual_seed(int(seed) * 7919 + 13)
+        aug = draw_augmentation(B, do_augment, mode, gen, dev)
+    out = prep_u8(I_u8, Ip_u8, pts1, aug, patch, want_rgb=want_rgb)
+    out.update(gt=gt, I_u8=I_u8, I_prime_u8=Ip_u8, aug=aug)
+    return out
+
+
+def prep_u8(I_u8, Ip_u8, pts1, aug, patch=128, want_rgb=False, want_plain=True):
+    """udh_prep_inputs_u8_ex on device tensors: augment + normalise + gray + patch gather in one pass."""
+    B, img_h, img_w = I_u8.shape[0], I_u8.shape[1], I_u8.shape[2]
+    dev = I_u8.device
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    I_gray = torch.empty(B, img_h, img_w, 1, device=dev)
+    I_rgb = torch.empty(B, img_h, img_w, 3, device=dev) if want_rgb else None
+    I1a = torch.empty(B, patch, patch, 1, device=dev); I2a = torch.empty_like(I1a)
+    I1 = torch.empty_like(I1a) if want_plain else None
+    I2 = torch.empty_like(I1a) if want_plain else None
+    origin = torch.empty(B, device=dev, dtype=torch.int32)
+    check(lib.udh_prep_inputs_u8_ex(p(I_u8), p(Ip_u8), p(pts1), p(aug), p(I_gray), p(I_rgb), p(I1), p(I2), p(I1a), p(I2a), p(origin),
+                                    B, img_h, img_w, patch, ops._stream()), "udh_prep_inputs_u8_ex")
+    out = dict(I1=I1 if want_plain else I1a, I2=I2 if want_plain else I2a, I1_aug=I1a, I2_aug=I2a, I_aug=I_gray, I_prime_aug=None,
+               pts1=pts1, patch_indices=origin)
+    if want_rgb:
+        out["I_aug_rgb"] = I_rgb
+    return out

@@ -95,14 +95,16 @@ class HostStepper(object):
 
     def step_u8(self, host_batch, train=True):
         """Same as step(), but the host hands over the DECODED uint8 images (what the reference dataloader holds before
-        normalising): normalisation, gray conversion and patch gather run on the device (udh_prep_inputs_u8)."""
+        normalising): augmentation (host_batch["aug_dev"], optional [B,11] device tensor), normalisation, gray conversion
+        and patch gather run on the device in one kernel (udh_prep_inputs_u8_ex)."""
         import ctypes
         from ._lib import check, lib
         eng = self.eng
         if self.u8_slots is None:
             B, Hh, W = eng.B, eng.img_h, eng.img_w
             self.u8_slots = [dict(I_u8=torch.empty(B, Hh, W, 3, device=eng.device, dtype=torch.uint8),
-                                  I_prime_u8=torch.empty(B, Hh, W, 3, device=eng.device, dtype=torch.uint8)) for _ in range(self.depth)]
+                                  I_prime_u8=torch.empty(B, Hh, W, 3, device=eng.device, dtype=torch.uint8),
+                                  I_gray=torch.empty(B, Hh, W, 1, device=eng.device)) for _ in range(self.depth)]
         slot = self.i % self.depth
         dst, u8 = self.slots[slot], self.u8_slots[slot]
         with torch.cuda.stream(self.copy_stream):
@@ -116,10 +118,13 @@ class HostStepper(object):
         self.h2d_bytes = 2 * host_batch["I_u8"].numel() + 2 * host_batch["pts1"].numel() * 4
         cur = torch.cuda.current_stream()
         cur.wait_event(self.ready[slot])
-        p = lambda t: ctypes.c_void_p(t.data_ptr())
-        check(lib.udh_prep_inputs_u8(p(u8["I_u8"]), p(u8["I_prime_u8"]), p(dst["pts1"]), p(dst["I_aug"]), p(dst["I1_aug"]),
-                                     p(dst["I2_aug"]), p(dst["patch_indices"]), eng.B, eng.img_h, eng.img_w, eng.Pz,
-                                     ctypes.c_void_p(cur.cuda_stream)), "udh_prep_inputs_u8")
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        # one fused pass: (augment,) normalise, gray, patch gather; the warp reads the GRAY plane (a third of the bytes of the
+        # fp32 3-channel tensor, which is never materialised on this path)
+        check(lib.udh_prep_inputs_u8_ex(p(u8["I_u8"]), p(u8["I_prime_u8"]), p(dst["pts1"]), p(host_batch.get("aug_dev")), p(u8["I_gray"]), None,
+                                        None, None, p(dst["I1_aug"]), p(dst["I2_aug"]), p(dst["patch_indices"]), eng.B, eng.img_h,
+                                        eng.img_w, eng.Pz, ctypes.c_void_p(cur.cuda_stream)), "udh_prep_inputs_u8_ex")
+        dst = dict(dst, I_aug=u8["I_gray"])
         out = eng.train_step(dst) if train else eng.eval_step(dst)
         self.free[slot].record(cur)
         res = torch.cat([out["h4p_metrics"], out["photo_losses"]])
