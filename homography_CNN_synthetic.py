@@ -109,10 +109,34 @@ def make_dirs(args, rank):
 
 
 def latest_checkpoint(model_dir, model_name):
-    """The reference saves to model_dir + model_name (string concat, :360) and restores from latest_checkpoint(model_dir)
-    (:315); here both sides use  <model_dir>/<model_name>-<step>.pt ."""
+    """The reference saves TF checkpoints to model_dir + model_name (string concat, :360) and restores from
+    tf.train.latest_checkpoint(model_dir) (:315).  Here both sides use  <model_dir>/<model_name>-<step>  as the prefix of a
+    TensorFlow V2 bundle (.index + .data-00000-of-00001, written without TensorFlow: tf_checkpoint.py) plus the `checkpoint`
+    state file; `.pt` files of round 1 are still found.  Returns (path, kind)."""
+    from unsuperviseddeephomographyral2018_b200 import tf_checkpoint as tfc
+    p = tfc.latest_checkpoint(model_dir)
+    if p and os.path.exists(p + ".index"):
+        return p, "tf"
+    c = glob.glob(os.path.join(model_dir, model_name + "-*.index"))
+    if c:
+        return max(c, key=lambda f: int(f.rsplit("-", 1)[1][:-6]))[:-6], "tf"
     c = glob.glob(os.path.join(model_dir, model_name + "-*.pt"))
-    return max(c, key=lambda f: int(f.rsplit("-", 1)[1][:-3])) if c else None
+    return (max(c, key=lambda f: int(f.rsplit("-", 1)[1][:-3])), "pt") if c else (None, None)
+
+
+def restore(eng, ck, kind, reset_step=False):
+    import torch
+    if kind == "tf":
+        eng.load_tf_checkpoint(ck, reset_step=reset_step)
+    else:
+        eng.load_state_dict(torch.load(ck, map_location="cpu"), reset_step=reset_step)
+
+
+def save(eng, args, step):
+    from unsuperviseddeephomographyral2018_b200 import tf_checkpoint as tfc
+    prefix = os.path.join(args.model_dir, "%s-%d" % (args.model_name, step))
+    eng.save_tf_checkpoint(prefix)
+    tfc.update_checkpoint_state(args.model_dir, prefix, keep=5)                 # Saver(max_to_keep=5), :303
 
 
 def dist_env():
@@ -153,9 +177,9 @@ def train(args):
     eng = en.HomographyEngine(per_gpu, args.patch_size, args.img_h, args.img_w, numeric=args.numeric, seed=args.seed,
                               lr=args.lr, min_lr=args.min_lr, loss_type=args.loss_type, process_group=pg, world_size=world)
     if args.resume:
-        ck = latest_checkpoint(args.model_dir, args.model_name)
+        ck, kind = latest_checkpoint(args.model_dir, args.model_name)
         if ck:
-            eng.load_state_dict(torch.load(ck, map_location="cpu"), reset_step=args.retrain)     # :314-317
+            restore(eng, ck, kind, reset_step=args.retrain)                                        # :314-317
     start = eng.global_step
     if rank == 0:
         print('===> Start step:', start)
@@ -184,9 +208,9 @@ def train(args):
                              % (step, sums["h_loss"] / den, sums["rec_loss"] / den, sums["ssim_loss"] / den, sums["l1_loss"] / den,
                                 sums["l1_smooth_loss"] / den, sums["ncc_loss"] / den, out["lr"], den * args.batch_size / (time.time() - t0)))
         if step and step % 1000 == 0 and rank == 0:                     # :359-360
-            torch.save(eng.state_dict(), os.path.join(args.model_dir, "%s-%d.pt" % (args.model_name, step)))
+            save(eng, args, step)
     if rank == 0:
-        torch.save(eng.state_dict(), os.path.join(args.model_dir, "%s-%d.pt" % (args.model_name, step)))
+        save(eng, args, step)                                           # :389
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -217,11 +241,11 @@ def test_homography(args):
     loader = dl.Dataloader(dparams, shuffle=True, synthetic_pairs=args.synthetic, seed=args.seed * 97 + rank + 12345, device="cuda")
     eng = en.HomographyEngine(per_gpu, args.patch_size, args.img_h, args.img_w, numeric=args.numeric, seed=args.seed,
                               loss_type=args.loss_type, process_group=pg, world_size=world)
-    ck = latest_checkpoint(args.model_dir, args.model_name)
+    ck, kind = latest_checkpoint(args.model_dir, args.model_name)
     if rank == 0:
         print(args.model_dir)
     if ck:
-        eng.load_state_dict(torch.load(ck, map_location="cpu"))
+        restore(eng, ck, kind)
     elif rank == 0:
         print('===> no checkpoint under %s: evaluating the seeded initial weights' % args.model_dir)
     tot = dict(h=0.0, rec=0.0, ssim=0.0, l1=0.0, fail=0.0)

@@ -117,3 +117,57 @@ def test_named_checkpoint_roundtrip(tmp_path):
     np.savez(str(tmp_path / "bad.npz"), **bad)
     with pytest.raises(ValueError):
         P.load_named_npz(str(tmp_path / "bad.npz"))
+
+
+def test_tf_checkpoint_v2_roundtrip_and_format(tmp_path):
+    """Dependency-free TensorFlow checkpoint V2 writer / reader: CRC-32C known answer, table framing
+    (footer magic, block CRCs), the reference graph's variable names incl. Adam slots and global_step, the NHWC-flatten fc1
+    layout, corruption detection, and the `checkpoint` state file of tf.train.Saver."""
+    import struct
+    from unsuperviseddeephomographyral2018_b200 import params as P, tf_checkpoint as tfc
+    assert tfc.crc32c(b"123456789") == 0xE3069283                          # CRC-32C (Castagnoli) check value
+    big = np.random.default_rng(0).integers(0, 256, size=200003, dtype=np.uint8)
+    assert tfc.crc32c(big) == (tfc._crc_update_small(0xFFFFFFFF, big.tolist()) ^ 0xFFFFFFFF)    # lane-parallel path == serial path
+    assert tfc.unmask_crc(tfc.mask_crc(0x12345678)) == 0x12345678
+    specs = P.param_specs()
+    n = P.total_floats(specs)
+    rng = np.random.default_rng(1)
+    flat = P.init_flat(5)
+    # fc1 rows follow the NHWC flatten order (h*16 + w)*128 + c: tag one element per (h, w, c) corner case
+    s1 = specs["model/fc1/fc1/weights"]
+    fc1 = flat[s1.offset:s1.offset + s1.size].reshape(s1.shape)
+    fc1[(3 * 16 + 5) * 128 + 7, 11] = 1234.5
+    m = rng.normal(size=n).astype(np.float32) * 1e-3; v = rng.uniform(0, 1e-4, size=n).astype(np.float32)
+    variables = tfc.engine_state_to_variables(flat, m, v, 4321, specs)
+    assert variables["model/conv_block1/conv1/weights"].shape == (3, 3, 2, 64) and variables["model/fc1/fc1/weights"].shape == (32768, 1024)
+    assert "model/fc2/fc2/biases/Adam_1" in variables and variables["Variable"].dtype == np.int32 and int(variables["Variable"]) == 4321
+    assert abs(float(variables["beta1_power"]) - 0.9 ** 4322) < 1e-12
+    prefix = str(tmp_path / "m" / "model.ckpt-4321")
+    tfc.write_checkpoint(prefix, variables)
+    idx = open(prefix + ".index", "rb").read()
+    assert struct.unpack("<Q", idx[-8:])[0] == 0xdb4775248b80fb57            # LevelDB table magic
+    assert os.path.getsize(prefix + ".data-00000-of-00001") == sum(a.nbytes for a in variables.values())
+    back = tfc.read_checkpoint(prefix)
+    assert set(back) == set(variables)
+    for k in variables:
+        assert back[k].dtype == variables[k].dtype and np.array_equal(back[k], variables[k]), k
+    f2, m2, v2, step = tfc.variables_to_engine_state(back, specs, n)
+    assert step == 4321 and np.array_equal(f2, flat) and np.array_equal(m2[s1.offset:s1.offset + s1.size], m[s1.offset:s1.offset + s1.size])
+    assert back["model/fc1/fc1/weights"][(3 * 16 + 5) * 128 + 7, 11] == np.float32(1234.5)
+    # a flipped byte in the data shard is caught by the per-tensor CRC; a truncated index by the footer check
+    with open(prefix + ".data-00000-of-00001", "r+b") as f:
+        f.seek(1000); b = f.read(1); f.seek(1000); f.write(bytes([b[0] ^ 0xFF]))
+    with pytest.raises(ValueError):
+        tfc.read_checkpoint(prefix)
+    open(str(tmp_path / "bad.index"), "wb").write(idx[:-9])
+    open(str(tmp_path / "bad.data-00000-of-00001"), "wb").write(b"")
+    with pytest.raises(ValueError):
+        tfc.read_checkpoint(str(tmp_path / "bad"))
+    # inference-only checkpoint (no slots): parameters load, optimiser state is reported absent
+    small = {k: a for k, a in variables.items() if "/Adam" not in k and "power" not in k}
+    tfc.write_checkpoint(str(tmp_path / "inf"), small)
+    f3, m3, v3, step3 = tfc.variables_to_engine_state(tfc.read_checkpoint(str(tmp_path / "inf")), specs, n)
+    assert m3 is None and v3 is None and step3 == 4321 and np.array_equal(f3, flat)
+    # Saver state file
+    tfc.update_checkpoint_state(str(tmp_path / "m"), prefix)
+    assert tfc.latest_checkpoint(str(tmp_path / "m")) == prefix

@@ -129,6 +129,27 @@ class HomographyEngine(object):
     def import_named(self, path):
         self.load_flat(P.load_named_npz(path, self.Pz))
 
+    def save_tf_checkpoint(self, prefix, with_optimizer=True):
+        """TensorFlow checkpoint V2 bundle (<prefix>.index / .data-00000-of-00001) with the reference graph's variable names,
+        Adam slots and global_step — what tf.train.Saver writes at code/homography_CNN_synthetic.py:360 (tf_checkpoint.py)."""
+        from . import tf_checkpoint as tfc
+        m = self.adam_m.cpu().numpy() if with_optimizer else None
+        v = self.adam_v.cpu().numpy() if with_optimizer else None
+        tfc.write_checkpoint(prefix, tfc.engine_state_to_variables(self.params.cpu().numpy(), m, v, self.global_step, self.specs))
+
+    def load_tf_checkpoint(self, prefix, reset_step=False):
+        """Restore from a TensorFlow checkpoint V2 bundle (e.g. the reference's published models): parameters, and Adam slots /
+        global_step when present (train_saver.restore, code/homography_CNN_synthetic.py:314-317)."""
+        from . import tf_checkpoint as tfc
+        flat, m, v, step = tfc.variables_to_engine_state(tfc.read_checkpoint(prefix), self.specs, self.params.numel())
+        self.load_flat(flat)
+        if m is not None:
+            self.adam_m.copy_(torch.as_tensor(m)); self.adam_v.copy_(torch.as_tensor(v))
+        if step is not None and not reset_step:
+            self.global_step = step
+        elif reset_step:
+            self.global_step = 0
+
     def state_dict(self):
         return OrderedDict(params=self.params.cpu(), adam_m=self.adam_m.cpu(), adam_v=self.adam_v.cpu(),
                            global_step=self.global_step, patch_size=self.Pz)
