@@ -130,3 +130,38 @@ def test_fused_prep_kernel_augmentation_vs_oracle():
         assert torch.equal(got["I1_aug"][1], got["I1"][1]) and torch.equal(got["I2_aug"][1], got["I2"][1])
         # an augmented sample really changed, and saturates like the reference (x ** gamma on 0..255 clips at 255)
         assert (got["I1_aug"][0] - got["I1"][0]).abs().max() > 0.05
+
+
+def test_real_data_path_gtless_finetune_and_correspondence_test(tmp_path):
+    """homography_CNN_real.py end to end on the synthetic stand-in at the real-data geometry (142x190 images): a synthetic
+    model is saved as a TensorFlow checkpoint, --finetune restores it with the step reset and trains WITHOUT ground truth
+    (l1_loss), the new checkpoint lands in --save_model_dir, and --mode test prints the correspondence-metric table."""
+    _need_gpu()
+    from unsuperviseddeephomographyral2018_b200 import engine, params, tf_checkpoint as tfc
+    load_dir, save_dir = str(tmp_path / "syn"), str(tmp_path / "real")
+    eng = engine.HomographyEngine(2, seed=4, numeric="fp32")
+    eng.global_step = 999
+    os.makedirs(os.path.join(load_dir, "l1_loss_normalize"))
+    prefix = os.path.join(load_dir, "l1_loss_normalize", "model.ckpt-999")
+    eng.save_tf_checkpoint(prefix)
+    tfc.update_checkpoint_state(os.path.dirname(prefix), prefix)
+    common = ["--num_gpus", "1", "--synthetic", "64", "--batch_size", "8", "--seed", "4", "--load_model_dir", load_dir + "/", "--save_model_dir", save_dir + "/",
+              "--log_dir", str(tmp_path / "log") + "/", "--results_dir", str(tmp_path / "res") + "/"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "homography_CNN_real.py"), "--mode", "train", "--max_iterations", "12"] + common,
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "Finetune from" in r.stdout and "h_loss" not in [ln for ln in r.stdout.splitlines() if ln.startswith("Train")][-1]
+    ck = tfc.latest_checkpoint(os.path.join(save_dir, "l1_loss_normalize"))
+    assert ck and ck.endswith("model.ckpt-11")                                 # the step was reset to 0 by --finetune
+    v = tfc.read_checkpoint(ck)
+    assert int(v["Variable"]) == 12
+    w0 = eng.named_parameters()["model/conv_block4/conv2/weights"].cpu().numpy()
+    assert np.abs(v["model/conv_block4/conv2/weights"] - w0).max() > 0          # it trained (from the restored weights) ...
+    assert np.abs(v["model/conv_block4/conv2/weights"] - w0).max() < 12 * 1.1e-4   # ... by at most lr per step
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "homography_CNN_real.py"), "--mode", "test", "--do_augment", "0"] + common,
+                       capture_output=True, text=True, timeout=900, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    lines = r.stdout.splitlines()
+    i = next(k for k, ln in enumerate(lines) if ln.startswith("|Steps"))
+    step, h_loss, l1_loss, fail_pct = [float(x) for x in lines[i + 1].split()]
+    assert int(step) == 7 and 0 < h_loss < 30 and 0 < l1_loss < 2 and 0 <= fail_pct <= 100

@@ -171,3 +171,39 @@ def test_tf_checkpoint_v2_roundtrip_and_format(tmp_path):
     # Saver state file
     tfc.update_checkpoint_state(str(tmp_path / "m"), prefix)
     assert tfc.latest_checkpoint(str(tmp_path / "m")) == prefix
+
+
+def test_real_data_correspondence_metric_and_flags():
+    """Real-data path: the correspondence metric of code/homography_CNN_real.py:578-612 restated in NumPy
+    (against hand-built cases), and the entry script's flags / directory rules (:64-124)."""
+    import torch
+    from oracle import oracle as O
+    from unsuperviseddeephomographyral2018_b200 import real_metrics as rm, dataloader as dl
+    rng = np.random.default_rng(0)
+    # getPerspectiveTransform == the reference's DLT (h33 = 1) and maps the four points exactly
+    src = np.array([[24., 7.], [152., 7.], [152., 135.], [24., 135.]]); dst = src + rng.uniform(-20, 20, size=(4, 2))
+    H = rm.get_perspective_transform(src, dst)
+    assert abs(H[2, 2] - 1) < 1e-15 and np.abs(rm.perspective_transform(src, H) - dst).max() < 1e-9
+    assert np.abs(H - O.solve_dlt(torch.tensor(src.reshape(1, 8)), torch.tensor((dst - src).reshape(1, 8)))[0].numpy()).max() < 1e-9
+    # a perfect prediction gives ~0 error; a zero prediction gives exactly the identity error (and is not a "failure")
+    pts1 = np.array([[24., 7., 152., 7., 152., 135., 24., 135.]])
+    gt = rng.integers(-7, 8, size=(1, 8)).astype(np.float64)
+    r = 240.0 / 142.0
+    Hf = rm.get_perspective_transform((pts1.reshape(4, 2) * r).astype(np.float32), ((pts1 + gt).reshape(4, 2) * r).astype(np.float32))
+    c1 = np.stack([rng.uniform(40, 280, 4), rng.uniform(40, 200, 4)], 1)
+    c2 = rm.perspective_transform(c1, np.linalg.inv(Hf))
+    corr = np.concatenate([c1.reshape(-1), c2.reshape(-1)])[None] * 2.0
+    (h, ident, failed), = rm.correspondence_errors(gt, pts1, corr)
+    assert h < 1e-4 and not failed and ident > 0.5
+    (h0, ident0, failed0), = rm.correspondence_errors(np.zeros((1, 8)), pts1, corr)
+    assert abs(h0 - ident0) < 1e-9 and abs(ident0 - np.sqrt(np.mean((c1 - c2) ** 2))) < 1e-9 and not failed0
+    (h1, ident1, failed1), = rm.correspondence_errors(-3 * gt, pts1, corr)       # a prediction worse than identity is bounded
+    assert failed1 and h1 == ident1
+    # flags and directory rules
+    import homography_CNN_real as real
+    a = real.resolve_paths(real.build_parser().parse_args(["--data_path", "/d/", "--save_model_dir", "/m/real/", "--load_model_dir", "/m/syn/"]))
+    assert (a.img_h, a.img_w, a.full_img_h, a.full_img_w, a.patch_size) == (142, 190, 240, 320, 128)
+    assert a.finetune is True and a.gt_file is None and a.loss_type == "l1_loss" and a.numeric == "bf16x3"
+    assert a.load_model_dir == "/m/syn/l1_loss_normalize" and a.save_model_dir == "/m/real/l1_loss_normalize"
+    assert a.test_gt_file == "/d/test_gt.txt" and a.filenames_file == "/d/train_real.txt"
+    assert dl.extended_dataloader_params._fields[-2:] == ('full_img_h', 'full_img_w')

@@ -28,6 +28,23 @@ dataloader_params = namedtuple('parameters',
                                'do_augment,')
 
 
+# real-data set: a sample consists of full-size images, network-size images and the patch (code/dataloader.py:26-39)
+extended_dataloader_params = namedtuple('extended_parameters',
+                                        'data_path,'
+                                        'filenames_file,'
+                                        'pts1_file,'
+                                        'gt_file,'
+                                        'mode,'
+                                        'batch_size,'
+                                        'img_h,'
+                                        'img_w,'
+                                        'patch_size,'
+                                        'augment_list,'
+                                        'do_augment,'
+                                        'full_img_h,'
+                                        'full_img_w')
+
+
 def count_text_lines(path):
     """utils/utils.py:358-362."""
     with open(path, 'r') as f:
@@ -91,6 +108,80 @@ class Dataloader(object):
             out.append(self._order[self._cursor]); self._cursor += 1
         return np.array(out)
 
+    def _disk_batch_extended(self):
+        """Real-data samples (code/dataloader.py:146-200): FULL-size images are read, augmented and normalised at full
+        size, then AREA-resized to the network size; the ground truth (test only) is four hand-picked correspondences
+        (16 numbers), not a 4-point displacement.  JPEG decode, augmentation and resize run on the host as in the reference."""
+        import cv2
+        p = self.params
+        B, P, Hh, W, FH, FW = p.batch_size, p.patch_size, p.img_h, p.img_w, p.full_img_h, p.full_img_w
+        idx = self._next_indices(B)
+        mean, std = np.array(synthetic.MEAN_I, np.float32), np.array(synthetic.STD_I, np.float32)
+        I_aug = np.empty((B, Hh, W, 3), np.float32); Ip_aug = np.empty_like(I_aug); I_pl = np.empty_like(I_aug); Ip_pl = np.empty_like(I_aug)
+        full_I = np.empty((B, FH, FW, 3), np.uint8); full_Ip = np.empty_like(full_I)
+        for j, i in enumerate(idx):
+            name = self.names[i][1] if len(self.names[i]) > 1 else self.names[i][0]
+            pair = []
+            for sub in ("I", "I_prime"):
+                im = cv2.imread(os.path.join(p.data_path, sub, name), cv2.IMREAD_COLOR)
+                if im is None:
+                    raise IOError("cannot read %s" % os.path.join(p.data_path, sub, name))
+                im = cv2.cvtColor(im, cv2.COLOR_BGR2RGB)
+                if im.shape[0] != FH or im.shape[1] != FW:
+                    im = cv2.resize(im, (FW, FH), interpolation=cv2.INTER_AREA)
+                pair.append(im)
+            full_I[j], full_Ip[j] = pair
+            a, b = pair[0].astype(np.float32), pair[1].astype(np.float32)
+            aa, ba = a, b
+            if self._rng.uniform(0, 1) > (1 - p.do_augment):                                      # :163-169
+                draw = lambda: (self._rng.uniform(0.8, 1.2), self._rng.uniform(0.5, 2.0), self._rng.uniform(0.8, 1.2, size=3).astype(np.float32))
+                g, br, c = draw()
+                aa = np.clip(a ** np.float32(g) * np.float32(br) * c, 0, 255)
+                if self.mode != 'train':
+                    g, br, c = draw()                                                             # disjoint noise in test
+                ba = np.clip(b ** np.float32(g) * np.float32(br) * c, 0, 255)
+            rs = lambda t: cv2.resize((t - mean) / std, (W, Hh), interpolation=cv2.INTER_AREA) if (FH != Hh or FW != W) else (t - mean) / std
+            I_pl[j], Ip_pl[j], I_aug[j], Ip_aug[j] = rs(a), rs(b), rs(aa), rs(ba)
+        dev = self.device
+        pts1 = torch.tensor(self.pts1[idx], dtype=torch.float32, device=dev)
+        x0 = pts1[:, 0].long(); y0 = pts1[:, 1].long()
+        yy, xx = torch.meshgrid(torch.arange(P, device=dev), torch.arange(P, device=dev), indexing="ij")
+        pidx = ((yy[None] + y0[:, None, None]) * W + (xx[None] + x0[:, None, None])).reshape(B, -1)
+        t = lambda a: torch.from_numpy(a).to(dev)
+        g = lambda a: torch.gather(t(a).mean(dim=3).reshape(B, -1), 1, pidx).reshape(B, P, P, 1).contiguous()
+        out = dict(I1=g(I_pl), I2=g(Ip_pl), I1_aug=g(I_aug), I2_aug=g(Ip_aug), I_aug=t(I_aug).contiguous(), I_prime_aug=t(Ip_aug).contiguous(),
+                   pts1=pts1, gt=None, patch_indices=pidx.to(torch.int32).contiguous(), full_I=full_I, full_I_prime=full_Ip)
+        if self.gt is not None:
+            if self.gt.shape[1] == 16:
+                out["gt_corr"] = self.gt[idx].astype(np.float32)                                  # four correspondences (test set)
+            else:
+                out["gt"] = torch.tensor(self.gt[idx], dtype=torch.float32, device=dev)
+        return out
+
+    def _synthetic_real_batch(self):
+        """Stand-in for the (private) aerial data at the real-data geometry (142x190 images, 128 patches): on-device
+        synthetic pairs; training batches carry NO ground truth (gt-less l1 training), test batches carry four
+        correspondences per pair in the frame the reference clicked them on (2x the full image)."""
+        p = self.params
+        rho = min(self.rho, (p.img_h - p.patch_size) // 2, (p.img_w - p.patch_size) // 2)
+        b = synthetic.make_batch_fast(p.batch_size, seed=self.seed * 1000003 + self._step, img_h=p.img_h, img_w=p.img_w, patch=p.patch_size,
+                                      rho=rho, device=self.device, do_augment=float(p.do_augment), mode=self.mode)
+        if self.mode != 'train':
+            from . import real_metrics as rm
+            r = float(p.full_img_h) / float(p.img_h)
+            rng = np.random.default_rng(self.seed * 7 + self._step)
+            pts1, gt = b["pts1"].cpu().numpy().astype(np.float64), b["gt"].cpu().numpy().astype(np.float64)
+            corr = np.zeros((p.batch_size, 16), np.float32)
+            for j in range(p.batch_size):
+                H = rm.get_perspective_transform((pts1[j].reshape(4, 2) * r).astype(np.float32), ((pts1[j] + gt[j]).reshape(4, 2) * r).astype(np.float32))
+                c1 = np.stack([rng.uniform(40, p.full_img_w - 40, 4), rng.uniform(40, p.full_img_h - 40, 4)], 1)
+                c2 = rm.perspective_transform(c1, np.linalg.inv(H))
+                corr[j] = np.concatenate([c1.reshape(-1), c2.reshape(-1)]) * 2.0                 # clicked on 480x640 frames
+            b["gt_corr"] = corr
+        b["gt_4pt"] = b["gt"]
+        b["gt"] = None                                                                            # the real path never sees a 4-point gt
+        return b
+
     def _disk_batch(self):
         p = self.params
         B, P, Hh, W = p.batch_size, p.patch_size, p.img_h, p.img_w
@@ -120,7 +211,10 @@ class Dataloader(object):
     # ---- public ---------------------------------------------------------------------------------------------------
     def next_batch(self):
         p = self.params
-        if self.synthetic_pairs:
+        extended = hasattr(p, "full_img_h")
+        if extended:
+            b = self._synthetic_real_batch() if self.synthetic_pairs else self._disk_batch_extended()
+        elif self.synthetic_pairs:
             # on-device generator + fused augment / normalise / gray / crop (four kernel launches per batch); photometric
             # augmentation as the reference: probability do_augment, joint in train, disjoint in test
             b = synthetic.make_batch_fast(p.batch_size, seed=self.seed * 1000003 + self._step, img_h=p.img_h, img_w=p.img_w,
