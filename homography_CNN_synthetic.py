@@ -184,6 +184,10 @@ def train(args):
     if rank == 0:
         print('===> Start step:', start)
     sums = dict(h_loss=0.0, rec_loss=0.0, ssim_loss=0.0, l1_loss=0.0, l1_smooth_loss=0.0, ncc_loss=0.0)
+    writer = None
+    if rank == 0:
+        from unsuperviseddeephomographyral2018_b200 import tb_events
+        writer = tb_events.SummaryWriter(args.log_dir)                  # tf.summary.FileWriter(args.log_dir, ...), :300
     t0 = time.time()
     step = start
     for step in range(start, start + args.num_total_steps):
@@ -207,6 +211,16 @@ def train(args):
                     progress('Train: 1, step %d, h_loss %4.3f, rec_loss %4.3f, ssim_loss %.6f. l1_loss %.6f, l1_smooth_loss %.6f, ncc_loss %.6f, lr %.6f | %.1f pairs/s'
                              % (step, sums["h_loss"] / den, sums["rec_loss"] / den, sums["ssim_loss"] / den, sums["l1_loss"] / den,
                                 sums["l1_smooth_loss"] / den, sums["ncc_loss"] / den, out["lr"], den * args.batch_size / (time.time() - t0)))
+        if step % 1000 == 0:                                            # TensorBoard scalars, :285-293,356-358
+            d = eng.losses_dict(out)
+            if world > 1:
+                t = torch.tensor([d[k] for k in sums], device="cuda", dtype=torch.float64)
+                torch.distributed.all_reduce(t); t /= world
+                d.update(dict(zip(sums, t.tolist())))
+            if writer:
+                sc = {"Losses/Learning_rate": out["lr"]}
+                sc.update({"Losses/Total_" + k: d[k] for k in sums})
+                writer.add_scalars(sc, step)
         if step and step % 1000 == 0 and rank == 0:                     # :359-360
             save(eng, args, step)
     if rank == 0:

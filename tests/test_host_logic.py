@@ -207,3 +207,19 @@ def test_real_data_correspondence_metric_and_flags():
     assert a.load_model_dir == "/m/syn/l1_loss_normalize" and a.save_model_dir == "/m/real/l1_loss_normalize"
     assert a.test_gt_file == "/d/test_gt.txt" and a.filenames_file == "/d/train_real.txt"
     assert dl.extended_dataloader_params._fields[-2:] == ('full_img_h', 'full_img_w')
+
+
+def test_tensorboard_event_file_roundtrip(tmp_path):
+    """The scalars the reference logs every 1000 steps (code/homography_CNN_synthetic.py:285-293,356-358) as a TFRecord /
+    Event-proto file written without TensorFlow: framing CRCs, file_version header, tags, steps, values."""
+    from unsuperviseddeephomographyral2018_b200 import tb_events
+    w = tb_events.SummaryWriter(str(tmp_path / "log"))
+    tags = ["Losses/Learning_rate"] + ["Losses/Total_%s" % k for k in ("h_loss", "rec_loss", "ssim_loss", "l1_loss", "l1_smooth_loss", "ncc_loss")]
+    w.add_scalars({t: 0.5 + i for i, t in enumerate(tags)}, 0)
+    w.add_scalars({"Losses/Learning_rate": 1e-4}, 1000)
+    w.close()
+    raw = open(w.path, "rb").read()
+    assert b"brain.Event:2" in raw[:64] and os.path.basename(w.path).startswith("events.out.tfevents.")
+    ev = tb_events.read_events(w.path)
+    assert [s for s, _ in ev] == [0, 1000] and list(ev[0][1]) == tags
+    assert ev[0][1]["Losses/Total_ncc_loss"] == 6.5 and abs(ev[1][1]["Losses/Learning_rate"] - 1e-4) < 1e-10
