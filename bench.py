@@ -169,6 +169,7 @@ def run_ours(args):
     pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_MAX_CTAS", "32")                  # bound the allreduce kernel to the SMs the conv4_x backward leaves free
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
     numeric = args.numeric

@@ -255,6 +255,11 @@ unsigned long long udh_launch_count(void);
  * that the NCCL allreduce kernel overlapping the backward gets its own SMs instead of displacing persistent CTAs (a
  * displaced CTA would only start after another one finishes, i.e. serialise its whole share of the work). */
 int udh_set_sm_reserve(int n);
+/* Same, but only for the backward kernels of conv4_1 / conv4_2 (the launches that run while the fully connected gradients
+ * are being all-reduced on the communication stream).  A persistent kernel with a static item schedule that finds n of its
+ * SMs taken by the NCCL kernel runs those CTAs in a second wave (2x its time); with <= 2 items per CTA these four launches
+ * lose nothing by starting on (SMs - n) CTAs, so reserving NCCL's CTA count here removes the collision. */
+int udh_set_sm_reserve_top(int n);
 int udh_prof_enable(int on);
 int udh_prof_reset(void);
 int udh_prof_num_tags(void);

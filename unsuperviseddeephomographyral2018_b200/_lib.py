@@ -101,6 +101,7 @@ SIGNATURES = {
     "udh_warp_image_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "udh_launch_count": (c_ulonglong, []),
     "udh_set_sm_reserve": (c_int, [c_int]),
+    "udh_set_sm_reserve_top": (c_int, [c_int]),
     "udh_prof_enable": (c_int, [c_int]),
     "udh_prof_reset": (c_int, []),
     "udh_prof_num_tags": (c_int, []),

@@ -22,6 +22,8 @@ enum ProfTag {
 };
 extern unsigned long long g_launches;
 extern int g_sm_reserve;      // SMs the persistent tensor-core kernels leave free (udh_set_sm_reserve)
+extern int g_sm_reserve_top;  // SMs the conv4_x backward kernels leave free (udh_set_sm_reserve_top): these few launches run
+                              // while the fc-gradient allreduce occupies SMs; they have <= 2 items per CTA either way
 // CTAs a persistent one-CTA-per-SM kernel should launch on the current device
 inline int persistent_ctas() {
   int dev = 0, sms = 148;

@@ -228,7 +228,7 @@ __global__ void pool_bwd_x3_kernel(const uint32_t* __restrict__ codes, const uin
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
-template <int N_OUT, int CB, int T, int FA, int FW, int FO>
+template <int N_OUT, int CB, int T, int FA, int FW, int FO, bool WIDE = false>
 int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out,
                    uint16_t* out_limbs, float* out_f32, int relu, int B, int H, int W, float out_scale, cudaStream_t st) {
   tc::ConvGeom g;
@@ -250,11 +250,11 @@ int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, co
   uint64_t dimsO[2] = {(uint64_t)2 * N_OUT, (uint64_t)g.Q}, strO[2] = {2, (uint64_t)2 * N_OUT * 2};
   uint32_t boxO[2] = {64, 32};
   TRY(tc::make_tmap_bf16(&tmOut, out_limbs, 2, dimsO, strO, boxO));
-  using S = tc::ConvX3Smem<N_OUT, CB, T>;
+  using S = tc::ConvX3Smem<N_OUT, CB, T, WIDE>;
   const int stages = S::stages(g.abuf_rows);
   UDH_REQUIRE(stages >= 2, "tc conv x3: activation rows (%d x %d blocks) leave no room for the weight ring", g.abuf_rows, 2 * CB);
   const size_t smem = S::fixed_bytes(g.abuf_rows) + (size_t)stages * S::kWStageBytes;
-  auto kern = tc::tc_conv_x3_kernel<N_OUT, CB, T, FA, FW, FO>;
+  auto kern = tc::tc_conv_x3_kernel<N_OUT, CB, T, FA, FW, FO, WIDE>;
   UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = persistent_ctas();
   const int grid = g.num_items < sms ? g.num_items : sms;
@@ -266,6 +266,8 @@ int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, co
 template <int FA, int FW, int FO>
 int tc_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out,
                uint16_t* out_limbs, float* out_f32, int relu, int B, int H, int W, int cin, int cout, cudaStream_t st) {
+  static const int wide = [] { const char* e = getenv("UDH_X3_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (cin == 64 && cout == 64 && wide) return launch_conv_x3<64, 1, 2, FA, FW, FO, true>(x, wpk, bias, mask_bits, mask_out, out_limbs, out_f32, relu, B, H, W, 1.0f, st);
   if (cin == 64 && cout == 64 && W >= 128) return launch_conv_x3<64, 1, 3, FA, FW, FO>(x, wpk, bias, mask_bits, mask_out, out_limbs, out_f32, relu, B, H, W, 1.0f, st);
   if (cin == 64 && cout == 64) return launch_conv_x3<64, 1, 4, FA, FW, FO>(x, wpk, bias, mask_bits, mask_out, out_limbs, out_f32, relu, B, H, W, 1.0f, st);
   if (cin == 64 && cout == 128) return launch_conv_x3<128, 1, 2, FA, FW, FO>(x, wpk, bias, mask_bits, mask_out, out_limbs, out_f32, relu, B, H, W, 1.0f, st);
@@ -457,9 +459,12 @@ int x3_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     ProfScope ps(PROF_TC_PREP, st);        // (the mirrored weight packs were made by the forward of this step)
     TRY(pad_cast_x3(gA, U16(tcw, L.G[7]), B, P / 8, P / 8, 128, true, st));
   }
+  const int reserve_all = g_sm_reserve;
+  struct RestoreReserve { int v; ~RestoreReserve() { g_sm_reserve = v; } } restore_reserve{reserve_all};
   for (int i = 7; i >= 0; --i) {
     const int s = P / kConv[i].div;
     const int cin = kConv[i].cin, cout = kConv[i].cout;
+    g_sm_reserve = (i >= 6 && g_sm_reserve_top > reserve_all) ? g_sm_reserve_top : reserve_all;   // see udh_set_sm_reserve_top
     {
       ProfScope ps(PROF_CONV_WGRAD0 + i, st);
       if (i == 0) TRY(conv1_x3_wgrad(I1, I2, U16(tcw, L.G[0]), grads + poff[0], grads + poff[1], B, s, s, st));

@@ -14,6 +14,11 @@
 // (hi + lo of all 9 taps do not fit next to the activations); each ring block is reused by the T tiles of the item.
 //   warp 0: weight-ring producer | warp 1: MMA issuer | warp 2: TMEM allocator | warp 3: activation producer |
 //   warps 4-11: epilogue (two per TMEM lane quarter, as in the bf16 kernel).
+// Phase order: HI first (its first MMA initialises the accumulators), then LO.
+// WIDE (64 -> 64 channels): an (M128,N64,K16) MMA is capped at ~50 clk by the A-operand fetch (64 % of the tensor peak), so
+// phase HI issues ONE N = 128 MMA per k-step against the ring stage [W_hi | W_lo] (64 clk, full rate) into a MAIN and an AUX
+// accumulator (adjacent TMEM columns) instead of two N = 64 MMAs (100 clk); phase LO adds A_lo x W_hi into MAIN; the epilogue
+// reads MAIN + AUX.  Two accumulators per tile limit an item to T = 2 tiles (2 sets x 2 tiles x 128 columns = 512).
 #pragma once
 #include "conv_tc_kernels.cuh"
 
@@ -22,9 +27,9 @@ namespace tc {
 
 constexpr int kX3MaxStages = 6;
 
-template <int N_OUT, int CB, int T>
+template <int N_OUT, int CB, int T, bool WIDE = false>
 struct ConvX3Smem {
-  static constexpr int kWStageBytes = N_OUT * 128;
+  static constexpr int kWStageBytes = N_OUT * 128 * (WIDE ? 2 : 1);
   // fixed part: alignment slack + both limbs of the A rows + epilogue staging + barriers
   static size_t fixed_bytes(int abuf_rows) { return 1024 + (size_t)2 * CB * abuf_rows * 128 + kEpiStageBytes + 256; }
   static int stages(int abuf_rows) {
@@ -34,7 +39,7 @@ struct ConvX3Smem {
   }
 };
 
-template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O>
+template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O, bool WIDE = false>
 __global__ void __launch_bounds__(384, 1)
 tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
@@ -45,7 +50,11 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
   const int abuf_bytes = g.abuf_rows * 128;                       // one 64-channel block of one limb
   uint8_t* sA = base;                                             // [2 limbs][CB][abuf_rows][128]
   uint8_t* sW = base + (size_t)2 * CB * abuf_bytes;               // [stages][N_OUT][128]
-  uint8_t* sEpi = sW + (size_t)stages * N_OUT * 128;              // [4 quarters][32 rows][128 B]
+  static_assert(!WIDE || (N_OUT == 64 && T <= 2), "WIDE: 64 output channels, two accumulators per tile");
+  constexpr int kAcc = WIDE ? 2 : 1;                              // accumulators per tile (MAIN | AUX)
+  constexpr int kTileCols = N_OUT * kAcc;                         // TMEM columns per tile
+  constexpr int kStageBytes = N_OUT * 128 * kAcc;                 // one ring stage: [W_hi] or [W_hi | W_lo]
+  uint8_t* sEpi = sW + (size_t)stages * kStageBytes;              // [4 quarters][32 rows][128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + kEpiStageBytes);
   uint64_t* a_full = bars;            // [2] per limb (0 = hi, 1 = lo)
   uint64_t* a_empty = bars + 2;       // [2]
@@ -56,9 +65,9 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kX3MaxStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTmemCols = (2 * T * N_OUT <= 32) ? 32 : (2 * T * N_OUT <= 64) ? 64 : (2 * T * N_OUT <= 128) ? 128
-                            : (2 * T * N_OUT <= 256) ? 256 : 512;
-  static_assert(2 * T * N_OUT <= 512, "accumulators exceed TMEM");
+  constexpr int kTmemCols = (2 * T * kTileCols <= 32) ? 32 : (2 * T * kTileCols <= 64) ? 64 : (2 * T * kTileCols <= 128) ? 128
+                            : (2 * T * kTileCols <= 256) ? 256 : 512;
+  static_assert(2 * T * kTileCols <= 512, "accumulators exceed TMEM");
   static_assert(T <= 4, "mask prefetch registers are sized for T <= 4");
 
   if (threadIdx.x == 0) {
@@ -87,7 +96,7 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
         const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * T * 128;
 #pragma unroll 1
         for (int li = 0; li < 2; ++li) {
-          const int l = 1 - li;                                   // consumption order: lo limb first
+          const int l = li;                                       // consumption order: hi limb first
           mbar_wait(&a_empty[l], (it & 1) ^ 1);
           mbar_arrive_expect_tx(&a_full[l], (uint32_t)(CB * abuf_bytes));
           for (int cb = 0; cb < CB; ++cb) {
@@ -105,34 +114,39 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     // ===================================== weight-ring producer =====================================
     if (lane == 0) {
       uint32_t ws = 0, wpar = 1;                                  // first pass over the ring: the slots are free
-      auto push = [&](int block) {
+      auto push = [&](int block, int nblocks) {                  // `nblocks` consecutive [N_OUT][64] blocks into one stage
         mbar_wait(&w_empty[ws], wpar);
-        mbar_arrive_expect_tx(&w_full[ws], N_OUT * 128);
-        tma_load_2d(sW + (size_t)ws * N_OUT * 128, &tmW, 0, block * N_OUT, &w_full[ws]);
+        mbar_arrive_expect_tx(&w_full[ws], (uint32_t)(nblocks * N_OUT * 128));
+        for (int i = 0; i < nblocks; ++i)
+          tma_load_2d(sW + (size_t)ws * kStageBytes + (size_t)i * N_OUT * 128, &tmW, 0, (block + i) * N_OUT, &w_full[ws]);
         if (++ws == (uint32_t)stages) { ws = 0; wpar ^= 1u; }
       };
       for (int it = 0; it < my_items; ++it) {
-        for (int kb = 0; kb < 9 * CB; ++kb) push(kb * 2);                       // phase LO: A_lo x W_hi
-        for (int kb = 0; kb < 9 * CB; ++kb) { push(kb * 2); push(kb * 2 + 1); }    // phase HI: A_hi x W_hi, A_hi x W_lo
+        for (int kb = 0; kb < 9 * CB; ++kb) {                                     // phase HI: A_hi x W_hi, A_hi x W_lo
+          if (WIDE) push(kb * 2, 2);
+          else { push(kb * 2, 1); push(kb * 2 + 1, 1); }
+        }
+        for (int kb = 0; kb < 9 * CB; ++kb) push(kb * 2, 1);                      // phase LO: A_lo x W_hi
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     // The whole warp stays converged (descriptors live in uniform registers); one elected lane issues.
     constexpr uint32_t idesc = make_idesc_f16kind(128, N_OUT, 0, 0, FMT_A, FMT_W);
+    constexpr uint32_t idesc_wide = make_idesc_f16kind(128, 2 * N_OUT, 0, 0, FMT_A, FMT_W);
     const uint32_t a_addr0 = smem_u32(sA), w_addr0 = smem_u32(sW);
     // ring position as a running (stage, parity) pair and taps as running (ky, kx) counters: the issue loop of this single
     // warp is the serial resource of the kernel, so it carries no integer division and no per-block address rebuild
     uint32_t ws = 0, wpar = 0;
-    const uint32_t w_stage_units = (uint32_t)(N_OUT * 128) >> 4;
+    const uint32_t w_stage_units = (uint32_t)kStageBytes >> 4;
     const uint32_t w_lo0 = desc_lo(w_addr0, 16);
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
       mbar_wait(&t_empty[b], ((it >> 1) & 1) ^ 1);
-      const uint32_t d0 = tmem_base + (uint32_t)(b * T * N_OUT);
+      const uint32_t d0 = tmem_base + (uint32_t)(b * T * kTileCols);
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
-        const int l = 1 - ph;                                     // phase 0 consumes the lo limb, phase 1 the hi limb
+        const int l = ph;                                         // phase 0 consumes the hi limb, phase 1 the lo limb
         mbar_wait(&a_full[l], it & 1);
         tc_fence_after();
         // descriptor (low word) of tap (0,0), channel block 0 of this limb: rows start at hh - Wp - 1
@@ -148,17 +162,18 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
             for (int cb = 0; cb < CB; ++cb) {
 #pragma unroll
               for (int wl = 0; wl < 2; ++wl) {
-                if (wl == 1 && ph == 0) continue;                 // phase LO multiplies with W_hi only
+                if (wl == 1 && (ph == 1 || WIDE)) continue;       // phase LO multiplies with W_hi only; WIDE: one [hi | lo] stage
                 mbar_wait(&w_full[ws], wpar);
                 tc_fence_after();
                 const uint32_t a_lo = a_tap + (uint32_t)cb * cb_units;
                 const uint32_t w_lo = w_lo0 + ws * w_stage_units;
+                const uint32_t id = (WIDE && ph == 0) ? idesc_wide : idesc;
                 if (elect_one()) {
 #pragma unroll
                   for (int t = 0; t < T; ++t) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)     // +1024 sixteen-byte units per tile, +2 per 32-byte k-step
-                      umma_bf16(d0 + (uint32_t)(t * N_OUT), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), idesc,
+                      umma_bf16(d0 + (uint32_t)(t * kTileCols), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), id,
                                 (first | (uint32_t)(k > 0)) ? 1u : 0u);
                   }
                   umma_commit(&w_empty[ws]);
@@ -223,7 +238,13 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
         for (int hf = 0; hf < N_OUT / 64; ++hf) {
           const int c = hf * 2 + eg;
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * N_OUT + c * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * kTileCols + c * 32), v);
+          if (WIDE) {                                             // MAIN (A.W_hi terms) + AUX (A_hi.W_lo)
+            float u[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)((b * T + t) * kTileCols + N_OUT + c * 32), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += u[j];
+          }
           if (out_scale != 1.0f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= out_scale;

@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...) {
 
 unsigned long long g_launches = 0;
 int g_sm_reserve = 0;
+int g_sm_reserve_top = 0;
 
 namespace {
 const char* kTagNames[PROF_NUM_TAGS] = {
@@ -144,6 +145,12 @@ extern "C" unsigned long long udh_launch_count(void) { return udh::g_launches; }
 extern "C" int udh_set_sm_reserve(int n) {
   UDH_REQUIRE(n >= 0 && n < 128, "udh_set_sm_reserve: bad value %d", n);
   udh::g_sm_reserve = n;
+  return UDH_OK;
+}
+
+extern "C" int udh_set_sm_reserve_top(int n) {
+  UDH_REQUIRE(n >= 0 && n < 128, "udh_set_sm_reserve_top: bad value %d", n);
+  udh::g_sm_reserve_top = n;
   return UDH_OK;
 }
 

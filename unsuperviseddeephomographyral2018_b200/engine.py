@@ -91,6 +91,8 @@ class HomographyEngine(object):
         if world_size > 1:
             import os
             check(lib.udh_set_sm_reserve(int(os.environ.get("UDH_SM_RESERVE", "0"))), "udh_set_sm_reserve")
+            # the conv4_x backward launches overlap the fc-gradient allreduce: leave NCCL's SMs to it (udh.h)
+            check(lib.udh_set_sm_reserve_top(int(os.environ.get("UDH_SM_RESERVE_TOP", "32"))), "udh_set_sm_reserve_top")
         # static per-step outputs of the one-call step (udh_step_forward_backward): reused every step
         B, Pz, dev = self.B, self.Pz, self.device
         self._sb = dict(h4p=torch.zeros(B, 8, device=dev), H=torch.zeros(B, 3, 3, device=dev), pred=torch.zeros(B, Pz, Pz, 1, device=dev),
