@@ -228,6 +228,18 @@ __global__ void pool_bwd_x3_kernel(const uint32_t* __restrict__ codes, const uin
 }
 
 // ---------------------------------------------------------------------------------------------------- launchers
+template <int N_OUT, int CB, int T, int FA, int FW, int FO, bool WIDE, int STAGES>
+int launch_conv_x3_impl(const CUtensorMap& tmA128, const CUtensorMap& tmAhh, const CUtensorMap& tmW, const CUtensorMap& tmOut, const tc::ConvGeom& g,
+                        int stages, size_t smem, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out, float* out_f32, int relu,
+                        float out_scale, cudaStream_t st) {
+  auto kern = tc::tc_conv_x3_kernel<N_OUT, CB, T, FA, FW, FO, WIDE, STAGES>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = persistent_ctas();
+  const int grid = g.num_items < sms ? g.num_items : sms;
+  launch_chain(kern, dim3(grid), dim3(384), smem, st, tmA128, tmAhh, tmW, tmOut, g, stages, bias, mask_bits, mask_out, out_f32, relu, out_scale);
+  return check_launch("tc_conv_x3_kernel");
+}
+
 template <int N_OUT, int CB, int T, int FA, int FW, int FO, bool WIDE = false>
 int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out,
                    uint16_t* out_limbs, float* out_f32, int relu, int B, int H, int W, float out_scale, cudaStream_t st) {
@@ -251,15 +263,25 @@ int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, co
   uint32_t boxO[2] = {64, 32};
   TRY(tc::make_tmap_bf16(&tmOut, out_limbs, 2, dimsO, strO, boxO));
   using S = tc::ConvX3Smem<N_OUT, CB, T, WIDE>;
-  const int stages = S::stages(g.abuf_rows);
+  int stages = S::stages(g.abuf_rows);
   UDH_REQUIRE(stages >= 2, "tc conv x3: activation rows (%d x %d blocks) leave no room for the weight ring", g.abuf_rows, 2 * CB);
-  const size_t smem = S::fixed_bytes(g.abuf_rows) + (size_t)stages * S::kWStageBytes;
-  auto kern = tc::tc_conv_x3_kernel<N_OUT, CB, T, FA, FW, FO, WIDE>;
-  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int sms = persistent_ctas();
-  const int grid = g.num_items < sms ? g.num_items : sms;
-  launch_chain(kern, dim3(grid), dim3(384), smem, st, tmA128, tmAhh, tmW, tmOut, g, stages, bias, mask_bits, mask_out, out_f32, relu, out_scale);
-  return check_launch("tc_conv_x3_kernel");
+  // static ring (unrolled issue loop) when a depth of 6 or 3 fits: both divide the 18*CB (WIDE) / 27*CB stages of an item
+  // (measured: the 128-channel / CB = 2 instances are better off with the deeper runtime ring, so only WIDE uses it)
+  static const int static_env = [] { const char* e = getenv("UDH_X3_STATIC_RING"); return (e && e[0] == '0') ? 0 : 1; }();
+  const int use_static = WIDE ? static_env : 0;
+  constexpr int kSPI = (WIDE ? 18 : 27) * CB;
+  if constexpr (kSPI % 6 == 0) if (use_static && stages >= 6) {
+    stages = 6;
+    return launch_conv_x3_impl<N_OUT, CB, T, FA, FW, FO, WIDE, 6>(tmA128, tmAhh, tmW, tmOut, g, stages, S::fixed_bytes(g.abuf_rows) + (size_t)stages * S::kWStageBytes,
+                                                                  bias, mask_bits, mask_out, out_f32, relu, out_scale, st);
+  }
+  if (use_static && stages >= 3) {
+    stages = 3;
+    return launch_conv_x3_impl<N_OUT, CB, T, FA, FW, FO, WIDE, 3>(tmA128, tmAhh, tmW, tmOut, g, stages, S::fixed_bytes(g.abuf_rows) + (size_t)stages * S::kWStageBytes,
+                                                                  bias, mask_bits, mask_out, out_f32, relu, out_scale, st);
+  }
+  return launch_conv_x3_impl<N_OUT, CB, T, FA, FW, FO, WIDE, 0>(tmA128, tmAhh, tmW, tmOut, g, stages, S::fixed_bytes(g.abuf_rows) + (size_t)stages * S::kWStageBytes,
+                                                                bias, mask_bits, mask_out, out_f32, relu, out_scale, st);
 }
 
 // one 3x3 conv on limb streams; (cin -> cout, image width) selects the kernel instance.  FA/FW/FO: limb formats.

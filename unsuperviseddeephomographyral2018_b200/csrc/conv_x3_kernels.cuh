@@ -39,7 +39,11 @@ struct ConvX3Smem {
   }
 };
 
-template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O, bool WIDE = false>
+// STAGES > 0: the ring depth is a compile-time constant that divides the stages of an item, so every item starts at ring
+// slot 0 and the MMA issue loop is fully unrolled with static slots, parities and tap offsets (ncu of the dynamic loop:
+// the weights were never late, but ~90 bookkeeping instructions of the single issuing lane between two groups of MMAs let
+// the tensor pipe drain — 54 % active where the issue mix allows 84 %).  STAGES == 0: runtime ring (any depth).
+template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O, bool WIDE = false, int STAGES = 0>
 __global__ void __launch_bounds__(384, 1)
 tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
@@ -140,6 +144,56 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     uint32_t ws = 0, wpar = 0;
     const uint32_t w_stage_units = (uint32_t)kStageBytes >> 4;
     const uint32_t w_lo0 = desc_lo(w_addr0, 16);
+    if constexpr (STAGES > 0) {
+      constexpr int kHiStages = (WIDE ? 9 : 18) * CB, kSPI = kHiStages + 9 * CB;      // ring stages of phase HI / of an item
+      static_assert(kSPI % STAGES == 0, "the static ring depth must divide the stages of an item");
+      constexpr int kPasses = kSPI / STAGES;
+      const uint32_t cb_units = (uint32_t)abuf_bytes >> 4;
+      const uint32_t wp8 = (uint32_t)g.Wp * 8;                    // one image row of taps, in sixteen-byte units
+      const uint32_t a_hi0 = desc_lo(a_addr0 + (uint32_t)(g.hh - g.Wp - 1) * 128, 16);
+      const uint32_t a_lo0 = desc_lo(a_addr0 + (uint32_t)CB * abuf_bytes + (uint32_t)(g.hh - g.Wp - 1) * 128, 16);
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const uint32_t itpar = (kPasses & 1) ? (uint32_t)(it & 1) : 0u;
+        mbar_wait(&t_empty[b], ((it >> 1) & 1) ^ 1);
+        const uint32_t d0 = tmem_base + (uint32_t)(b * T * kTileCols);
+        // ONE elected lane runs the whole item (waits included): no per-stage election / reconvergence between MMA groups
+        if (elect_one()) {
+          mbar_wait(&a_full[0], it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < kSPI; ++j) {
+            const bool hi = j < kHiStages;
+            const int jj = hi ? j : j - kHiStages;
+            const int kb = (hi && !WIDE) ? (jj >> 1) : jj;        // (tap, cb) index
+            const int tap = kb / CB, cb = kb - tap * CB;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            const int s = j % STAGES;
+            if (j == kHiStages) {                                 // phase HI done: release the hi rows, take the lo rows
+              umma_commit(&a_empty[0]);
+              mbar_wait(&a_full[1], it & 1);
+              tc_fence_after();
+            }
+            mbar_wait(&w_full[s], ((uint32_t)(j / STAGES) + itpar) & 1u);
+            tc_fence_after();
+            const uint32_t a_lo = (hi ? a_hi0 : a_lo0) + (uint32_t)ky * wp8 + (uint32_t)(kx * 8) + (uint32_t)cb * cb_units;
+            const uint32_t w_lo = w_lo0 + (uint32_t)s * w_stage_units;
+            const uint32_t id = (WIDE && hi) ? idesc_wide : idesc;
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d0 + (uint32_t)(t * kTileCols), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), id,
+                          (j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&w_empty[s]);
+          }
+          umma_commit(&a_empty[1]);
+          umma_commit(&t_full[b]);
+        }
+        __syncwarp();
+      }
+    } else
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
       mbar_wait(&t_empty[b], ((it >> 1) & 1) ^ 1);
