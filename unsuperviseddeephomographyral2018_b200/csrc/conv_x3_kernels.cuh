@@ -198,31 +198,32 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
       const int b = it & 1;
       mbar_wait(&t_empty[b], ((it >> 1) & 1) ^ 1);
       const uint32_t d0 = tmem_base + (uint32_t)(b * T * kTileCols);
+      const uint32_t ws0 = ws, wpar0 = wpar;
+      if (elect_one()) {                                          // one elected lane runs the whole item (waits included)
 #pragma unroll 1
-      for (int ph = 0; ph < 2; ++ph) {
-        const int l = ph;                                         // phase 0 consumes the hi limb, phase 1 the lo limb
-        mbar_wait(&a_full[l], it & 1);
-        tc_fence_after();
-        // descriptor (low word) of tap (0,0), channel block 0 of this limb: rows start at hh - Wp - 1
-        const uint32_t a_tap0 = desc_lo(a_addr0 + (uint32_t)(l * CB) * abuf_bytes + (uint32_t)(g.hh - g.Wp - 1) * 128, 16);
-        const uint32_t cb_units = (uint32_t)abuf_bytes >> 4;
-        uint32_t first = ph == 0 ? 0u : 1u;                       // the very first MMA of the item overwrites the accumulators
+        for (int ph = 0; ph < 2; ++ph) {
+          const int l = ph;                                       // phase 0 consumes the hi limb, phase 1 the lo limb
+          mbar_wait(&a_full[l], it & 1);
+          tc_fence_after();
+          // descriptor (low word) of tap (0,0), channel block 0 of this limb: rows start at hh - Wp - 1
+          const uint32_t a_tap0 = desc_lo(a_addr0 + (uint32_t)(l * CB) * abuf_bytes + (uint32_t)(g.hh - g.Wp - 1) * 128, 16);
+          const uint32_t cb_units = (uint32_t)abuf_bytes >> 4;
+          uint32_t first = ph == 0 ? 0u : 1u;                     // the very first MMA of the item overwrites the accumulators
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {
+          for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll 1
-          for (int kx = 0; kx < 3; ++kx) {
-            const uint32_t a_tap = a_tap0 + (uint32_t)(ky * g.Wp + kx) * 8;      // 128-byte rows = 8 sixteen-byte units
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint32_t a_tap = a_tap0 + (uint32_t)(ky * g.Wp + kx) * 8;      // 128-byte rows = 8 sixteen-byte units
 #pragma unroll
-            for (int cb = 0; cb < CB; ++cb) {
+              for (int cb = 0; cb < CB; ++cb) {
 #pragma unroll
-              for (int wl = 0; wl < 2; ++wl) {
-                if (wl == 1 && (ph == 1 || WIDE)) continue;       // phase LO multiplies with W_hi only; WIDE: one [hi | lo] stage
-                mbar_wait(&w_full[ws], wpar);
-                tc_fence_after();
-                const uint32_t a_lo = a_tap + (uint32_t)cb * cb_units;
-                const uint32_t w_lo = w_lo0 + ws * w_stage_units;
-                const uint32_t id = (WIDE && ph == 0) ? idesc_wide : idesc;
-                if (elect_one()) {
+                for (int wl = 0; wl < 2; ++wl) {
+                  if (wl == 1 && (ph == 1 || WIDE)) continue;     // phase LO multiplies with W_hi only; WIDE: one [hi | lo] stage
+                  mbar_wait(&w_full[ws], wpar);
+                  tc_fence_after();
+                  const uint32_t a_lo = a_tap + (uint32_t)cb * cb_units;
+                  const uint32_t w_lo = w_lo0 + ws * w_stage_units;
+                  const uint32_t id = (WIDE && ph == 0) ? idesc_wide : idesc;
 #pragma unroll
                   for (int t = 0; t < T; ++t) {
 #pragma unroll
@@ -231,19 +232,23 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
                                 (first | (uint32_t)(k > 0)) ? 1u : 0u);
                   }
                   umma_commit(&w_empty[ws]);
+                  first = 1u;
+                  if (++ws == (uint32_t)stages) { ws = 0; wpar ^= 1u; }
                 }
-                __syncwarp();
-                first = 1u;
-                if (++ws == (uint32_t)stages) { ws = 0; wpar ^= 1u; }
               }
             }
           }
-        }
-        if (elect_one()) {
           umma_commit(&a_empty[l]);                               // this limb's rows are no longer read -> producer
           if (ph == 1) umma_commit(&t_full[b]);                   // accumulators of this item complete -> epilogue
         }
-        __syncwarp();
+      }
+      __syncwarp();
+      // the elected lane advanced its private copy of the ring position: every lane recomputes it (once per item)
+      {
+        constexpr uint32_t kSPI = (uint32_t)((WIDE ? 18 : 27) * CB);
+        const uint32_t tot = ws0 + kSPI;
+        ws = tot % (uint32_t)stages;
+        wpar = wpar0 ^ ((tot / (uint32_t)stages) & 1u);
       }
     }
   } else if (warp >= 4) {

@@ -109,77 +109,78 @@ tc_wgrad_x3_kernel(const __grid_constant__ CUtensorMap tmX128, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // whole warp converged; one elected lane issues (see conv_tc_kernels.cuh)
+    // One elected lane runs the whole MMA role (waits included); the per-group operand geometry (row shift of the first M
+    // block, leading-dimension offset to the second one, constant-block mode) does not depend on the item and is tabulated once.
     constexpr uint32_t idesc = make_idesc_f16kind(128, N_OUT, 1, 1, FMT_X, FMT_G);
     constexpr uint32_t idesc_ones = make_idesc_f16kind(64, N_OUT, 1, 1, FMT_X, FMT_G);
     const uint32_t ones_addr = smem_u32(sOnes), zeros_addr = smem_u32(sZeros);
-    for (int it = 0; it < my_items; ++it) {
-      const uint32_t par = it & 1;
-#pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const int xl = pass == 0 ? 1 : 0;                         // X limb of this pass
-        const int gl_ = pass == 2 ? 1 : 0;                        // G limb of this pass
-        if (pass == 0) { mbar_wait(&full[kXL], par); mbar_wait(&full[kGH], par); }
-        else if (pass == 1) mbar_wait(&full[kXH], par);
-        else mbar_wait(&full[kGL], par);
-        tc_fence_after();
-        const uint32_t x_addr = smem_u32(sX[xl]);
-        const uint32_t g_addr = smem_u32(sG[gl_]);
-        const uint32_t const_addr = xl ? zeros_addr : ones_addr;  // the constant-one channel has no lo limb
-#pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-#pragma unroll 1
-          for (int gi_l = 0; gi_l < g_count; ++gi_l) {
-            const int gi = g_begin + gi_l;
-            uint32_t a_start;
-            int lbo_mode = 0;                                     // 0: fixed lbo; 1: constant block (lbo recomputed per k-step)
-            uint32_t lbo = 0;
-            if (CBX == 1) {
-              const int tap0 = 2 * gi;
-              const int off0 = (tap0 / 3 - 1) * g.Wp + (tap0 % 3 - 1);
-              a_start = x_addr + (uint32_t)(g.hh + t * 128 + off0) * 128;
-              if (gi < 4) {
-                const int tap1 = tap0 + 1;
-                const int off1 = (tap1 / 3 - 1) * g.Wp + (tap1 % 3 - 1);
-                lbo = (uint32_t)(off1 - off0) * 128;
-              } else {
-                lbo_mode = 1;                                     // second M block = the constant rows (bias gradient)
-              }
-            } else if (gi < 9) {
-              const int off = (gi / 3 - 1) * g.Wp + (gi % 3 - 1);
-              a_start = x_addr + (uint32_t)(g.hh + t * 128 + off) * 128;
-              lbo = (uint32_t)xblk_bytes;                         // second M block = channels 64..127
-            } else {
-              if (xl) continue;                                   // ones group: X_hi passes only
-              a_start = ones_addr; lbo = 0; lbo_mode = 2;         // M = 64 rows of ones, same 2 KB for every k-step
-            }
-            const uint32_t id = (CBX == 2 && gi == 9) ? idesc_ones : idesc;
-            const uint32_t b_lo = desc_lo(g_addr + (uint32_t)t * 16384, (uint32_t)gblk_bytes);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(gi_l * N_OUT);
-            // the first MMA into an accumulator overwrites it: pass 0 (or pass 1 for the ones group, which skips pass 0)
-            const bool fresh = it == 0 && t == 0 && (pass == 0 || (CBX == 2 && gi == 9 && pass == 1));
-            if (elect_one()) {
+    if (elect_one()) {
+      int goff[4]; uint32_t glbo[4]; int gmode[4];               // mode 0: fixed lbo; 1: second M block = constant rows; 2: ones group (M = 64)
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {                     // 16 positions = 2048 bytes = 128 sixteen-byte units per k-step
+      for (int gi_l = 0; gi_l < 4; ++gi_l) {
+        const int gi = g_begin + gi_l;
+        goff[gi_l] = 0; glbo[gi_l] = 0; gmode[gi_l] = 0;
+        if (gi_l >= g_count) continue;
+        if (CBX == 1) {
+          const int tap0 = 2 * gi;
+          const int off0 = (tap0 / 3 - 1) * g.Wp + (tap0 % 3 - 1);
+          goff[gi_l] = off0;
+          if (gi < 4) {
+            const int tap1 = tap0 + 1;
+            glbo[gi_l] = (uint32_t)(((tap1 / 3 - 1) * g.Wp + (tap1 % 3 - 1)) - off0) * 128;
+          } else {
+            gmode[gi_l] = 1;
+          }
+        } else if (gi < 9) {
+          goff[gi_l] = (gi / 3 - 1) * g.Wp + (gi % 3 - 1);
+          glbo[gi_l] = (uint32_t)xblk_bytes;                      // second M block = channels 64..127
+        } else {
+          gmode[gi_l] = 2;
+        }
+      }
+      for (int it = 0; it < my_items; ++it) {
+        const uint32_t par = it & 1;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const int xl = pass == 0 ? 1 : 0;                       // X limb of this pass
+          const int gl_ = pass == 2 ? 1 : 0;                      // G limb of this pass
+          if (pass == 0) { mbar_wait(&full[kXL], par); mbar_wait(&full[kGH], par); }
+          else if (pass == 1) mbar_wait(&full[kXH], par);
+          else mbar_wait(&full[kGL], par);
+          tc_fence_after();
+          const uint32_t x_addr = smem_u32(sX[xl]);
+          const uint32_t g_addr = smem_u32(sG[gl_]);
+          const uint32_t const_addr = xl ? zeros_addr : ones_addr; // the constant-one channel has no lo limb
+#pragma unroll 1
+          for (int t = 0; t < T; ++t) {
+            const uint32_t b_lo = desc_lo(g_addr + (uint32_t)t * 16384, (uint32_t)gblk_bytes);
+#pragma unroll
+            for (int gi_l = 0; gi_l < 4; ++gi_l) {
+              if (gi_l >= g_count) continue;
+              const int mode = gmode[gi_l];
+              if (mode == 2 && xl) continue;                      // ones group: X_hi passes only
+              const uint32_t a_start = mode == 2 ? ones_addr : x_addr + (uint32_t)(g.hh + t * 128 + goff[gi_l]) * 128;
+              const uint32_t id = mode == 2 ? idesc_ones : idesc;
+              const uint32_t d_tmem = tmem_base + (uint32_t)(gi_l * N_OUT);
+              // the first MMA into an accumulator overwrites it: pass 0 (or pass 1 for the ones group, which skips pass 0)
+              const bool fresh = it == 0 && t == 0 && (pass == 0 || (mode == 2 && pass == 1));
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {                     // 16 positions = 2048 bytes per k-step
                 uint32_t a_lo;
-                if (lbo_mode == 0) a_lo = desc_lo(a_start + kk * 2048, lbo);
-                else if (lbo_mode == 1) a_lo = desc_lo(a_start + kk * 2048, const_addr - (a_start + kk * 2048));
+                if (mode == 0) a_lo = desc_lo(a_start + kk * 2048, glbo[gi_l]);
+                else if (mode == 1) a_lo = desc_lo(a_start + kk * 2048, const_addr - (a_start + kk * 2048));
                 else a_lo = desc_lo(a_start, 0);
                 umma_bf16(d_tmem, desc_from_lo(a_lo), desc_from_lo(b_lo + kk * 128), id, (fresh && kk == 0) ? 0u : 1u);
               }
             }
-            __syncwarp();
           }
-        }
-        if (elect_one()) {
           if (pass == 0) umma_commit(&empty[kXL]);
           else if (pass == 1) umma_commit(&empty[kGH]);
           else { umma_commit(&empty[kXH]); umma_commit(&empty[kGL]); }
         }
-        __syncwarp();
       }
+      umma_commit(acc_full);
     }
-    if (elect_one()) umma_commit(acc_full);
     __syncwarp();
   } else if (warp >= 4 && my_items > 0) {
     const int ew = warp - 4;
