@@ -287,6 +287,10 @@ int udh_debug_tc_wgrad(const float* x, const float* g, float* dW, float* db, voi
  * udh_cnn_activation names; *fp32_region_bytes (nullable) = size of the leading part of the workspace whose layout is common
  * to all numeric modes (activations, dropout masks, fc buffers), so a test can run the fp32 backward on this forward state. */
 int udh_debug_x3_materialize(void* ws, size_t ws_bytes, int B, int P, size_t* fp32_region_bytes, void* stream);
+/* conv1_2 of the UDH_NUMERIC_BF16X3 mode runs on row tiles by default (forward fused with pool1: the full-resolution
+ * activation is never stored; row-tile dgrad).  on = 0 selects the generic flattened-tile kernels + the separate pool kernel —
+ * tests compare the two paths and need the un-fused one to read conv1_2's activation. */
+int udh_debug_x3_set_rows(int on);
 size_t udh_debug_x3_scratch_bytes(int B, int H, int W, int cin, int cout);
 int udh_debug_x3_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W, int cin,
                       int cout, int relu, int dgrad, void* stream);

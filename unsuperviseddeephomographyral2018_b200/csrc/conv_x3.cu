@@ -284,6 +284,43 @@ int launch_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, co
                                                                 bias, mask_bits, mask_out, out_f32, relu, out_scale, st);
 }
 
+// conv1_2 on row tiles (64 -> 64 channels, 128-wide images): ROWS = 1 forward fused with pool1 (writes the pooled two-limb
+// stream + routing codes), ROWS = 2 the dgrad (ordinary epilogue).  See conv_x3_kernels.cuh.
+template <int ROWS, int FA, int FW, int FO>
+int launch_conv_x3_rows(const uint16_t* x, const uint16_t* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* codes_or_mask,
+                        uint16_t* out_limbs, int relu, int B, int H, int W, cudaStream_t st) {
+  UDH_REQUIRE(W == 128 && H % 2 == 0 && out_limbs, "tc conv x3 rows: needs W == 128, an even height and an output stream");
+  tc::ConvGeom g;
+  g.B = B; g.H = H; g.W = W; g.Hp = H + 2; g.Wp = W + 2;
+  g.Q = B * g.Hp * g.Wp;
+  g.hh = (g.Wp + 1 + 7) / 8 * 8;
+  g.num_items = B * (H / 2);
+  g.abuf_rows = 2 * 128 + 2 * g.hh;
+  UDH_REQUIRE(g.hh + g.Wp + 128 + g.Wp + 1 <= g.abuf_rows, "tc conv x3 rows: halo does not cover the second row tile");
+  CUtensorMap tmA128, tmAhh, tmW, tmOut;
+  uint64_t dimsA[2] = {128, (uint64_t)g.Q}, strA[2] = {2, 256};
+  uint32_t box128[2] = {64, 128}, boxhh[2] = {64, (uint32_t)g.hh}, boxO[2] = {64, 32};
+  TRY(tc::make_tmap_bf16(&tmA128, x, 2, dimsA, strA, box128));
+  TRY(tc::make_tmap_bf16(&tmAhh, x, 2, dimsA, strA, boxhh));
+  uint64_t dimsW[2] = {64, (uint64_t)18 * 64}, strW[2] = {2, 128};
+  uint32_t boxW[2] = {64, 64};
+  TRY(tc::make_tmap_bf16(&tmW, wpk, 2, dimsW, strW, boxW));
+  // ROWS = 1 stores the pooled stream with plain vector stores (the map is only a placeholder there)
+  TRY(tc::make_tmap_bf16(&tmOut, ROWS == 2 ? out_limbs : const_cast<uint16_t*>(x), 2, dimsA, strA, boxO));
+  using S = tc::ConvX3Smem<64, 1, 2, true>;
+  constexpr int kStages = 3;
+  const size_t smem = S::fixed_bytes(g.abuf_rows) + (size_t)kStages * S::kWStageBytes;
+  UDH_REQUIRE(smem <= 232448, "tc conv x3 rows: %zu bytes of shared memory exceed the 227 KiB limit", smem);
+  auto kern = tc::tc_conv_x3_kernel<64, 1, 2, FA, FW, FO, true, kStages, ROWS>;
+  UDH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int sms = persistent_ctas();
+  const int grid = g.num_items < sms ? g.num_items : sms;
+  // ROWS = 1: `out_f32` carries the pooled stream pointer and `mask_out` the routing codes
+  launch_chain(kern, dim3(grid), dim3(384), smem, st, tmA128, tmAhh, tmW, tmOut, g, kStages, bias, mask_bits, codes_or_mask,
+               ROWS == 1 ? reinterpret_cast<float*>(out_limbs) : (float*)nullptr, relu, 1.0f);
+  return check_launch("tc_conv_x3_kernel(rows)");
+}
+
 // one 3x3 conv on limb streams; (cin -> cout, image width) selects the kernel instance.  FA/FW/FO: limb formats.
 template <int FA, int FW, int FO>
 int tc_conv_x3(const uint16_t* x, const uint16_t* wpk, const float* bias, const uint32_t* mask_bits, uint32_t* mask_out,
@@ -433,6 +470,10 @@ int conv1_x3_wgrad(const float* I1, const float* I2, const uint16_t* G_limbs, fl
 
 inline uint16_t* U16(char* base, size_t off) { return reinterpret_cast<uint16_t*>(base + off); }
 
+// conv1_2 on row tiles (forward fused with pool1, row-tile dgrad): on by default, UDH_X3_ROWS=0 / udh_debug_x3_set_rows(0)
+// select the generic flattened-tile kernels + the separate pool kernel (tests compare the two)
+int g_x3_rows = [] { const char* e = getenv("UDH_X3_ROWS"); return (e && e[0] == '0') ? 0 : 1; }();
+
 }  // namespace
 
 int x3_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, const float* I2, void* ws, const size_t* act_off,
@@ -456,8 +497,15 @@ int x3_cnn_fwd_convs(const float* params, const size_t* poff, const float* I1, c
     ProfScope ps(PROF_CONV_FWD0, st);
     TRY(conv1_x3_fwd(I1, I2, params + poff[0], params + poff[1], U16(tcw, L.P[0]), reinterpret_cast<uint32_t*>(tcw + L.Mb[0]), B, P, P, st));
   }
+  const bool fuse_pool1 = g_x3_rows && P == 128;            // conv1_2 + pool1 in one kernel (row tiles need 128-wide images)
   for (int i = 1; i < 8; ++i) {
     const int s = P / kConv[i].div;
+    if (i == 1 && fuse_pool1) {
+      ProfScope ps(PROF_CONV_FWD0 + i, st);
+      TRY((launch_conv_x3_rows<1, kFwd, kFwd, kFwd>(U16(tcw, L.P[0]), U16(tcw, L.wf[1]), params + poff[3], nullptr,
+                                                    reinterpret_cast<uint32_t*>(tcw + L.Px[0]), U16(tcw, L.P[8]), 1, B, s, s, st)));
+      continue;
+    }
     {
       ProfScope ps(PROF_CONV_FWD0 + i, st);
       TRY((tc_conv_x3<kFwd, kFwd, kFwd>(U16(tcw, L.P[input_of(i)]), U16(tcw, L.wf[i]), params + poff[2 * i + 1], nullptr,
@@ -495,6 +543,12 @@ int x3_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
     if (i == 0) break;
     const bool below_is_pool = (i == 2 || i == 4 || i == 6);
     const int below = input_of(i);
+    if (i == 1 && g_x3_rows && P == 128) {
+      ProfScope ps(PROF_CONV_DGRAD0 + i, st);                 // conv1_2 dgrad on row tiles, ReLU mask of conv1_1 fused
+      TRY((launch_conv_x3_rows<2, kGrad, kGrad, kGrad>(U16(tcw, L.G[1]), U16(tcw, L.wd[1]), nullptr, reinterpret_cast<const uint32_t*>(tcw + L.Mb[0]),
+                                                       nullptr, U16(tcw, L.G[0]), 0, B, s, s, st)));
+      continue;
+    }
     {
       ProfScope ps(PROF_CONV_DGRAD0 + i, st);
       // dgrad = conv of G[i] with the mirrored kernel; ReLU mask of the layer below fused unless a pool sits between
@@ -517,6 +571,7 @@ int x3_materialize_acts(void* ws, const size_t* act_off, size_t tc_off, int B, i
   char* tcw = at<char>(ws, tc_off);
   for (int i = 0; i < 11; ++i) {
     if (i == 7) continue;                                    // conv4_2 is written in fp32 by the forward itself
+    if (i == 1 && P == 128 && g_x3_rows) continue;           // conv1_2 is fused with pool1: its full-resolution output is never stored
     const int s = i < 8 ? P / kConv[i].div : P >> (i - 7);
     const int c = i < 8 ? kConv[i].cout : (i == 10 ? 128 : 64);
     TRY(unpad_cast_x3(U16(tcw, L.P[i]), at<float>(ws, act_off[i]), B, s, s, c, false, st));
@@ -643,6 +698,11 @@ int x3_debug_conv1(const float* I1, const float* I2, const float* w, const float
 }
 
 }  // namespace udh
+
+extern "C" int udh_debug_x3_set_rows(int on) {
+  udh::g_x3_rows = on != 0;
+  return UDH_OK;
+}
 
 extern "C" size_t udh_debug_x3_scratch_bytes(int B, int H, int W, int cin, int cout) { return udh::x3_debug_scratch_bytes(B, H, W, cin, cout); }
 

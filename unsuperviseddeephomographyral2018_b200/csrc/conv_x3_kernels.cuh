@@ -43,7 +43,14 @@ struct ConvX3Smem {
 // slot 0 and the MMA issue loop is fully unrolled with static slots, parities and tap offsets (ncu of the dynamic loop:
 // the weights were never late, but ~90 bookkeeping instructions of the single issuing lane between two groups of MMAs let
 // the tensor pipe drain — 54 % active where the issue mix allows 84 %).  STAGES == 0: runtime ring (any depth).
-template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O, bool WIDE = false, int STAGES = 0>
+// ROWS (W == 128 images, 64 -> 64 channels, T == 2: conv1_2).  An item is the interior of two consecutive image rows
+// (2y, 2y+1): tile t starts at the first interior position of row 2y + t, i.e. the tiles are Wp (not 128) positions apart in
+// the same staged rows, no border position is computed, and the epilogue thread of column x holds both rows of that column.
+//   ROWS == 1: forward fused with the 2x2 max-pool — bias + ReLU, maximum (vertical in registers, horizontal with one lane
+//              exchange), then the POOLED two-limb stream and the 3-bit routing codes of the max-pool backward are written; the
+//              full-resolution activation (554 MB in this mode) is never written or re-read;
+//   ROWS == 2: the ordinary epilogue (bias / ReLU-backward mask / limb split / TMA store) on row tiles (the dgrad).
+template <int N_OUT, int CB, int T, int FMT_A, int FMT_W, int FMT_O, bool WIDE = false, int STAGES = 0, int ROWS = 0>
 __global__ void __launch_bounds__(384, 1)
 tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_constant__ CUtensorMap tmAhh,
                   const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, const ConvGeom g,
@@ -55,6 +62,11 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
   uint8_t* sA = base;                                             // [2 limbs][CB][abuf_rows][128]
   uint8_t* sW = base + (size_t)2 * CB * abuf_bytes;               // [stages][N_OUT][128]
   static_assert(!WIDE || (N_OUT == 64 && T <= 2), "WIDE: 64 output channels, two accumulators per tile");
+  static_assert(ROWS == 0 || (WIDE && STAGES > 0 && CB == 1 && T == 2), "row tiles: the WIDE static-ring instance with two tiles");
+  constexpr bool POOL = ROWS == 1;
+  // first position of an item and distance between its tiles (in positions)
+  auto item_q0 = [&](int item) { return ROWS ? ((item / (g.H >> 1)) * g.Hp + 2 * (item % (g.H >> 1)) + 1) * g.Wp + 1 : item * T * 128; };
+  const int tstep = ROWS ? g.Wp : 128;
   constexpr int kAcc = WIDE ? 2 : 1;                              // accumulators per tile (MAIN | AUX)
   constexpr int kTileCols = N_OUT * kAcc;                         // TMEM columns per tile
   constexpr int kStageBytes = N_OUT * 128 * kAcc;                 // one ring stage: [W_hi] or [W_hi | W_lo]
@@ -97,7 +109,7 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     // ===================================== activation producer =====================================
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
-        const int q0 = ((int)blockIdx.x + it * (int)gridDim.x) * T * 128;
+        const int q0 = item_q0((int)blockIdx.x + it * (int)gridDim.x);
 #pragma unroll 1
         for (int li = 0; li < 2; ++li) {
           const int l = li;                                       // consumption order: hi limb first
@@ -182,9 +194,9 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
 #pragma unroll
             for (int t = 0; t < T; ++t) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d0 + (uint32_t)(t * kTileCols), desc_from_lo(a_lo + t * 1024 + k * 2), desc_from_lo(w_lo + k * 2), id,
-                          (j > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)     // tiles are 128 rows (1024 units) apart, or one image row (Wp rows) on row tiles
+                umma_bf16(d0 + (uint32_t)(t * kTileCols), desc_from_lo(a_lo + (ROWS ? (uint32_t)t * wp8 : (uint32_t)(t * 1024)) + k * 2),
+                          desc_from_lo(w_lo + k * 2), id, (j > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&w_empty[s]);
           }
@@ -259,6 +271,60 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     const int eg = (warp - 4) >> 2;
     const int ew = (warp - 4) & 3;
     const int HpWp = g.Hp * g.Wp;
+    if constexpr (POOL) {
+      // thread = image column x (W == 128 == tile rows); warp group eg pools the 32-channel chunk eg
+      const int OH = g.H >> 1, OW = g.W >> 1;
+      const int x = ew * 32 + lane;
+      const int px = x >> 1, odd = x & 1;
+      uint16_t* out_pool = reinterpret_cast<uint16_t*>(out_f32);             // pooled two-limb stream [B][OH+2][OW+2][hi 64 | lo 64]
+      for (int it = 0; it < my_items; ++it) {
+        const int b = it & 1;
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int n = item / OH, yy = item - n * OH;
+        mbar_wait(&t_full[b], (it >> 1) & 1);
+        tc_fence_after();
+        uint16_t* prow = out_pool + (((size_t)n * (OH + 2) + yy + 1) * (OW + 2) + px + 1) * 128;
+        uint32_t* crow = mask_out + (((size_t)n * OH + yy) * OW + px) * 8;
+        const int c = eg;
+        float v0[32], v1[32], u[32];
+        const uint32_t tl = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * T * kTileCols + c * 32);
+        tmem_ld32(tl, v0);                  tmem_ld32(tl + N_OUT, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v0[j] += u[j];
+        tmem_ld32(tl + kTileCols, v1);      tmem_ld32(tl + kTileCols + N_OUT, u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v1[j] += u[j];
+        tc_fence_before();
+        mbar_arrive(&t_empty[b]);           // the accumulators are in registers: the MMA warp may overwrite this set
+        uint32_t code[4] = {0u, 0u, 0u, 0u};
+        float m[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float bj = __ldg(bias + c * 32 + j);
+          const float a = fmaxf(v0[j] + bj, 0.f), d = fmaxf(v1[j] + bj, 0.f);
+          // scan order of the 2x2 window: (row 0, x even)=0, (row 0, x odd)=1, (row 1, even)=2, (row 1, odd)=3;
+          // the first maximum wins: larger value, ties to the smaller index
+          float vs = a; uint32_t ks = (uint32_t)odd;
+          if (d > a) { vs = d; ks = 2u + (uint32_t)odd; }
+          const float vo = __shfl_xor_sync(0xffffffffu, vs, 1);
+          const uint32_t ko = __shfl_xor_sync(0xffffffffu, ks, 1);
+          const bool other = vo > vs || (vo == vs && ko < ks);
+          const float mv = other ? vo : vs;
+          const uint32_t mk = other ? ko : ks;
+          m[j] = mv;
+          code[j >> 3] |= (mv > 0.f ? mk : 4u) << (3 * (j & 7));
+        }
+        // both lanes of a pair hold the pooled pixel: the even lane stores channels 0-15 of this chunk, the odd 16-31
+        uint32_t ph_[8], pl_[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) split2<FMT_O>(odd ? m[16 + 2 * h] : m[2 * h], odd ? m[17 + 2 * h] : m[2 * h + 1], ph_[h], pl_[h]);
+        uint4* oh = reinterpret_cast<uint4*>(prow + c * 32 + odd * 16);
+        oh[0] = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]); oh[1] = make_uint4(ph_[4], ph_[5], ph_[6], ph_[7]);
+        uint4* ol = reinterpret_cast<uint4*>(prow + 64 + c * 32 + odd * 16);
+        ol[0] = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]); ol[1] = make_uint4(pl_[4], pl_[5], pl_[6], pl_[7]);
+        *reinterpret_cast<uint2*>(crow + c * 4 + odd * 2) = odd ? make_uint2(code[2], code[3]) : make_uint2(code[0], code[1]);
+      }
+    } else {
     uint8_t* stg = sEpi + ew * 4096;
     const uint32_t my_row = smem_u32(stg) + lane * 128;
     const int sw = lane & 7;
@@ -268,12 +334,12 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     for (int it = 0; it < my_items; ++it) {
       const int b = it & 1;
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
-      const int q0w0 = item * T * 128 + ew * 32;
+      const int q0w0 = item_q0(item) + ew * 32;
       // ReLU-backward mask words (1 bit / element) of all T tiles, requested before the accumulator wait
       uint32_t mbt[T][2];
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const int qt = q0w0 + t * 128 + lane;
+        const int qt = q0w0 + t * tstep + lane;
         const bool ok = mask_bits && qt < g.Q;
         if (N_OUT == 64) {
           mbt[t][0] = ok ? __ldg(mask_bits + (size_t)qt * 2 + eg) : 0u; mbt[t][1] = 0u;
@@ -286,7 +352,7 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < T; ++t) {
-        const int q0w = q0w0 + t * 128;
+        const int q0w = q0w0 + t * tstep;
         const int q = q0w + lane;
         const int n = q / HpWp, rem = q - n * HpWp;
         const int yp = rem / g.Wp, xp = rem - yp * g.Wp;
@@ -369,6 +435,7 @@ tc_conv_x3_kernel(const __grid_constant__ CUtensorMap tmA128, const __grid_const
     }
     if (issuer) bulk_wait0();
     __syncwarp();
+    }
   }
   tc_fence_before();
   __syncthreads();
