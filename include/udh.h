@@ -267,13 +267,9 @@ const char* udh_prof_tag_name(int tag);
 int udh_prof_read(int tag, float* total_ms, int* count);
 
 /* ---- debug / test entry points of the tensor-core path ---------------------------------------------------------
- * udh_debug_umma_probe: hardware probe of the TMA / tcgen05 descriptor conventions (csrc/tc_probe.cu).
+ * (the hardware probes of the TMA / tcgen05 conventions live in their own library: include/udh_probe.h, libudh_probe.so)
  * udh_debug_tc_conv: ONE tcgen05 3x3 convolution on fp32 NHWC tensors (pads + casts to bf16 internally), so tests can
  * compare the tensor-core kernel with a reference convolution layer by layer; dgrad != 0 runs the mirrored kernel. */
-int udh_debug_umma_probe(const void* A, int a_rows, const void* B, int b_rows, float* out, int mode, int use_bo, void* stream);
-/* CTA-pair (cta_group::2) probe, csrc/tc_probe2.cu: D[256][N] = A[256][64] . B[N][64]^T on a 2-CTA cluster; cycles[2]. */
-int udh_debug_umma2_probe(const void* A, const void* B, float* out, unsigned long long* cycles, int N, int pair,
-                          int remote_tma, int reps, int nacc, void* stream);
 size_t udh_debug_tc_conv_scratch_bytes(int B, int H, int W, int cin, int cout);
 int udh_debug_tc_conv(const float* x, const float* w, const float* bias, float* out, void* scratch, int B, int H, int W,
                       int cin, int cout, int relu, int dgrad, void* stream);

@@ -50,14 +50,15 @@ def test_tcgen05_descriptor_conventions(udh):
     A = torch.randn(144, 64, device="cuda", generator=g).bfloat16().contiguous()
     B = torch.randn(64, 64, device="cuda", generator=g).bfloat16().contiguous()
     out = torch.zeros(128, 512, device="cuda")
-    assert udh.L.udh_debug_umma_probe(P(A), 144, P(B), 64, P(out), 0, 0, None) == 0
+    probes = udh.lib.load_probes()                       # libudh_probe.so: the product library carries no probe kernels
+    assert probes.udh_debug_umma_probe(P(A), 144, P(B), 64, P(out), 0, 0, None) == 0
     torch.cuda.synchronize()
     for s in range(8):
         assert (out[:, 64 * s:64 * s + 64] - A[s:s + 128].float() @ B.float().t()).abs().max() < 1e-3
     G = torch.randn(128, 128, device="cuda", generator=g).bfloat16()
     Gb = torch.cat([G[:, :64], G[:, 64:]], dim=0).contiguous()
     X = torch.randn(144, 64, device="cuda", generator=g).bfloat16().contiguous()
-    assert udh.L.udh_debug_umma_probe(P(Gb), 256, P(X), 144, P(out), 1, 0, None) == 0
+    assert probes.udh_debug_umma_probe(P(Gb), 256, P(X), 144, P(out), 1, 0, None) == 0
     torch.cuda.synchronize()
     for s in range(8):
         assert (out[:, 64 * s:64 * s + 64] - G.float().t() @ X[s:s + 128].float()).abs().max() < 1e-3

@@ -1,13 +1,11 @@
-"""Hardware probe of the tcgen05 plumbing (see csrc/tc_probe.cu): prints max errors per mode / shift."""
+"""Hardware probe of the tcgen05 plumbing (see csrc/probes/tc_probe.cu): prints max errors per mode / shift."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 print("probe: importing torch", flush=True)
 import torch
 print("probe: torch imported, cuda", torch.cuda.is_available(), flush=True)
 from unsuperviseddeephomographyral2018_b200 import _lib
-lib = _lib.lib
-lib.udh_debug_umma_probe.restype = ctypes.c_int
-lib.udh_debug_umma_probe.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+lib = _lib.load_probes()      # libudh_probe.so (csrc/probes/)
 
 def run(A, B, mode, bo):
     print("probe: launching mode", mode, "bo", bo, flush=True)

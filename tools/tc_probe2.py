@@ -1,11 +1,11 @@
-"""CTA-pair (cta_group::2) tcgen05 probe (csrc/tc_probe2.cu): correctness of the paired MMA / multicast commit / remote TMA
+"""CTA-pair (cta_group::2) tcgen05 probe (csrc/probes/tc_probe2.cu): correctness of the paired MMA / multicast commit / remote TMA
 completion, and cycles per MMA of a long MMA stream with one CTA (M = 128) versus a pair (M = 256)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 print("probe2: importing torch", flush=True)
 import torch
 from unsuperviseddeephomographyral2018_b200 import _lib
-lib = _lib.lib
+lib = _lib.load_probes()      # libudh_probe.so (csrc/probes/)
 g = torch.Generator(device="cuda").manual_seed(3)
 A = torch.randn(256, 64, device="cuda", generator=g).bfloat16().contiguous()
 for N in (64, 128, 256):

@@ -86,8 +86,6 @@ SIGNATURES = {
     "udh_debug_x3_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "udh_debug_x3_conv1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                    c_int, c_void_p]),
-    "udh_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
-    "udh_debug_umma2_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "udh_debug_tc_conv_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "udh_debug_tc_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p]),
@@ -148,3 +146,13 @@ def prof_read_all():
         if n.value:
             out[lib.udh_prof_tag_name(t).decode()] = (ms.value, n.value)
     return out
+
+
+def load_probes():
+    """libudh_probe.so (include/udh_probe.h): hardware probes, built on demand, never loaded by the product path."""
+    plib = ctypes.CDLL(build_ext.build_probes())
+    plib.udh_debug_umma_probe.restype = c_int
+    plib.udh_debug_umma_probe.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]
+    plib.udh_debug_umma2_probe.restype = c_int
+    plib.udh_debug_umma2_probe.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
+    return plib

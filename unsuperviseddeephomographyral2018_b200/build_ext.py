@@ -88,5 +88,24 @@ def build(force=False, verbose=False, v=None):
     return lib
 
 
+PROBE_LIB = os.path.join(HERE, "libudh_probe.so")
+
+
+def build_probes(force=False):
+    """Hardware probes (csrc/probes/: TMA / tcgen05 descriptor conventions, CTA-pair MMAs, MMA issue rates) live in their OWN
+    library, libudh_probe.so, declared in include/udh_probe.h — the product library carries no debug kernels.  Links against
+    libudh.so for the shared error / launch-count helpers."""
+    lib = build()
+    srcs = sorted(glob.glob(os.path.join(CSRC, "probes", "*.cu")))
+    if not force and os.path.exists(PROBE_LIB) and all(os.path.getmtime(s) < os.path.getmtime(PROBE_LIB) for s in srcs) \
+            and os.path.getmtime(lib) < os.path.getmtime(PROBE_LIB):
+        return PROBE_LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    tmp = "%s.tmp.%d" % (PROBE_LIB, os.getpid())
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ["-shared", "-o", tmp] + srcs + ["-L" + HERE, "-l:libudh.so", "-Xlinker", "-rpath=$ORIGIN"])
+    os.replace(tmp, PROBE_LIB)
+    return PROBE_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -5,7 +5,7 @@
 //   mode 1: MN-major operands: G two blocks [128 px][64] (LBO = 16 KiB apart), X [a_rows px][64];
 //           D_s[co][ci] = sum_px G[px][co] * X[px+s][ci], M = 128, N = 64, K = 128 px (8 MMAs of K = 16).
 //   mode 2: M = 64 accumulator layout: D = A[0:64] . B^T, K-major, dumped raw.
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 namespace udh {
 namespace tc {

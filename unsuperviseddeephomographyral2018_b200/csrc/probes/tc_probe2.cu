@@ -7,7 +7,7 @@
 //                   mapa-translated barrier address + a remote expect_tx), the pattern a pipelined kernel needs.
 //   The MMA sequence (4 k-steps) is repeated `reps` times; the leader reports cycles per MMA, so the same kernel measures
 //   the shared-memory operand bandwidth relief of pairing (tools/tc_probe2.py compares with cta_group::1, pair = 0).
-#include "tc_common.cuh"
+#include "../tc_common.cuh"
 
 namespace udh {
 namespace tc {
