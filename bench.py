@@ -40,6 +40,7 @@ def parse():
                     help="auto = bf16x3, the tensor-core mode the parity tests certify (tests/test_gpu_x3.py)")
     ap.add_argument("--loss_type", default="h_loss")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dp-diag", default="", choices=["", "nocomm"], help="multi-GPU diagnosis only: 'nocomm' skips the gradient allreduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the short BASELINE configs[2]/[3] side measurements")
     return ap.parse_args()
@@ -172,6 +173,12 @@ def run_ours(args):
         os.environ.setdefault("NCCL_MAX_CTAS", "32")                  # bound the allreduce kernel to the SMs the conv4_x backward leaves free
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
+        if args.dp_diag == "nocomm":
+            # DIAGNOSTIC ONLY (the line is labelled and is not a bench value): skip the gradient allreduce so that the
+            # per-rank step times show the GPU-to-GPU spread the collective otherwise hides behind its implicit barrier.
+            _real_all_reduce = dist.all_reduce
+            torch.distributed.all_reduce = lambda t, op=dist.ReduceOp.SUM, group=None, async_op=False: (
+                _real_all_reduce(t, op=op, group=group) if op == dist.ReduceOp.MAX else None)
     numeric = args.numeric
     if numeric == "auto":
         numeric = "bf16x3"       # the parity-certified tensor-core mode is the headline; single-pass bf16 is a labelled side number
@@ -215,7 +222,11 @@ def run_ours(args):
     phases = _lib.prof_read_all()
     _lib.lib.udh_prof_enable(0)
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    ms_ranks = [ms_total / K]
     if world > 1:
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        ms_ranks = [float(x.item()) / K for x in g]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / K
@@ -332,6 +343,7 @@ def run_ours(args):
         parity = parity_check(torch, engine, numeric, dev)
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
+        "ms_per_step_ranks": [round(x, 4) for x in ms_ranks], "dp_diag": args.dp_diag or None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "parity": parity,
         "config": {"workload": "1-GPU train: synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s (BASELINE configs[1])" % args.loss_type,
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world, "numeric_mode": numeric,

@@ -160,8 +160,11 @@ def train(args):
                 syn.progress('Train: 1, step %d, rec_loss %4.3f, ssim_loss %.6f. l1_loss %.6f, l1_smooth_loss %.6f, lr %.6f | %.1f pairs/s'
                              % (step, sums["rec_loss"] / den, sums["ssim_loss"] / den, sums["l1_loss"] / den, sums["l1_smooth_loss"] / den,
                                 out["lr"], den * args.batch_size / (time.time() - t0)))
-        if step and step % 1000 == 0 and rank == 0:
-            syn.save(eng, save_args, step)
+        if step and step % 1000 == 0:
+            eng.sync_optimizer_state()                                  # collective: Adam's sharded m, v -> complete on every rank
+            if rank == 0:
+                syn.save(eng, save_args, step)
+    eng.sync_optimizer_state()
     if rank == 0:
         syn.save(eng, save_args, step)
     if world > 1:

@@ -222,8 +222,11 @@ def train(args):
                 sc = {"Losses/Learning_rate": out["lr"]}
                 sc.update({"Losses/Total_" + k: d[k] for k in sums})
                 writer.add_scalars(sc, step)
-        if step and step % 1000 == 0 and rank == 0:                     # :359-360
-            save(eng, args, step)
+        if step and step % 1000 == 0:                                   # :359-360
+            eng.sync_optimizer_state()                                  # collective: Adam's sharded m, v -> complete on every rank
+            if rank == 0:
+                save(eng, args, step)
+    eng.sync_optimizer_state()
     if rank == 0:
         save(eng, args, step)                                           # :389
     if world > 1:

@@ -260,6 +260,38 @@ int udh_set_sm_reserve(int n);
  * SMs taken by the NCCL kernel runs those CTAs in a second wave (2x its time); with <= 2 items per CTA these four launches
  * lose nothing by starting on (SMs - n) CTAs, so reserving NCCL's CTA count here removes the collision. */
 int udh_set_sm_reserve_top(int n);
+/* CTAs (of 256 threads) of the Adam launches that follow; 0 = the default, enough to fill the device.  An update that runs
+ * on a second stream underneath the conv backward is given one or two CTAs per SM so that the persistent tensor-core CTAs
+ * (one per SM, ~200 KB of shared memory, <= 256 threads) stay co-resident with it instead of queueing behind it. */
+int udh_set_adam_grid(int blocks);
+/* A point inside the conv backward for a second stream to start at: with layer = 7..0 (conv4_2..conv1_1; -1 = off) every
+ * conv backward that follows records an internal event on its stream right before the backward kernels of that layer, and
+ * udh_bwd_marker_wait(stream) makes `stream` wait for the most recent record (no-op before the first).  The engine uses it
+ * to run the fused gradient-reduce / Adam / weight-multicast kernel under the wide 64-channel layers' backward (tensor-bound)
+ * rather than under conv4_x / conv3_x (short, latency-bound launches that a co-running streaming kernel slows 3-5x). */
+int udh_set_bwd_marker(int layer);
+/* SMs the persistent backward kernels of the marker layer and of the layers below it leave free (0 = none): a kernel of
+ * 200+ KB of shared memory per CTA cannot share an SM with anything, so the second stream's kernel gets SMs of its own for
+ * the length of that window and is launched with exactly that many CTAs. */
+int udh_set_sm_reserve_marker(int n);
+int udh_bwd_marker_wait(void* stream);
+
+/* Row G + the optimiser for ONE rank's shard of a replicated tensor, over NVSwitch multicast memory (csrc/dp_update.cu):
+ * replaces, for fc1's weights, code/utils/utils.py:380-403 (gradient mean over the towers) followed by
+ * code/homography_CNN_synthetic.py:277-284 (apply_gradients).  mc_grads / mc_params are the MULTICAST addresses of the
+ * flat gradient / parameter buffers (symmetric allocations bound to one multicast object; the same float offsets as the
+ * local buffers), params / adam_m / adam_v the rank's local flat buffers.  For the floats [shard_begin, shard_begin +
+ * shard_count): g = sum over ranks (multimem.ld_reduce) * grad_scale; TF-1 Adam on the local m, v; the new fp32 value is
+ * stored to every replica (multimem.st), and so are its tensor-core limbs when mc_mirror (multicast address of the fc1
+ * weight mirror, udh_cnn_fc1_mirror; planes of mirror_count elements, hi then lo) is given: mirror_limbs = 1 (bf16) or 2
+ * (bf16x3), 0 with mc_mirror == NULL.  The gradient itself is left as is (fc1's weight gradient is stored, not accumulated).
+ * The caller orders the ranks: every rank's gradient must be final before any rank launches this, and every rank's launch
+ * must have completed before any replica is read (two symmetric-memory barriers on the stream, engine.py).  grid = CTAs of
+ * 512 threads (0 = one per SM). */
+int udh_dp_shard_update(const void* mc_grads, const float* params, void* mc_params, float* adam_m, float* adam_v,
+                        void* mc_mirror, size_t shard_begin, size_t shard_count, size_t mirror_begin, size_t mirror_count,
+                        int mirror_limbs, float alpha_t, float beta1, float beta2, float eps, float grad_scale, int grid,
+                        void* stream);
 int udh_prof_enable(int on);
 int udh_prof_reset(void);
 int udh_prof_num_tags(void);

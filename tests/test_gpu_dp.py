@@ -6,7 +6,10 @@ bf16 throughput mode:
     relative — for the fc slice and for the conv slice separately;
   * after three train steps the parameters are bit-identical on every rank;
   * one DP step equals single-GPU TF-Adam on the averaged gradient;
-  * data-parallel ranks draw different dropout masks.
+  * data-parallel ranks draw different dropout masks;
+  * the opt-in fused multicast path (switch-side gradient sum -> sharded Adam -> multicast of the new weights and their limbs, one
+    kernel) lands where the NCCL path lands, keeps the replicas' limb mirrors equal to the fp32 master, and its sharded
+    Adam state gathers to identical, complete buffers.
 Reference: code/utils/utils.py:380-403 (get_average_grads), code/homography_CNN_synthetic.py:199-207,277-284."""
 import json
 import os
@@ -39,3 +42,10 @@ def test_engine_data_parallel_two_ranks(numeric, tmp_path):
     assert res["rel_err_fc_slice"] <= tol and res["rel_err_conv_slice"] <= tol, res
     assert res["params_bit_identical_across_ranks"] and res["params_moved"] > 0 and res["global_step"] == 3
     assert res["dp_step_vs_manual_max_update_diff_over_lr"] <= 0.02, res
+    # Row G over NVSwitch multicast memory (csrc/dp_update.cu, UDH_DP_MODE=multicast): Adam's state is sharded and gathered
+    # on demand, replicas stay bit-identical, and three steps land where the NCCL path lands (the switch sums in another order)
+    assert res["default_path_is_nccl"] and res["nccl_engine_is_nccl"] and res["multicast_path"], res
+    assert res["multicast_params_bit_identical_across_ranks"], res
+    assert res["adam_m_identical_after_sync"] and min(res["adam_m_fc1_nonzero_fraction_per_shard"]) > 0.02, res
+    assert res["multicast_vs_nccl_rel_l2_of_update"] <= (1e-2 if numeric == "bf16x3" else 0.2), res    # three Adam steps: sign noise of near-zero gradients
+    assert res.get("mirror_matches_master", True), res

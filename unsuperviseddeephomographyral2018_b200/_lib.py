@@ -78,6 +78,8 @@ SIGNATURES = {
                                      c_int, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),
     "udh_adam_step_mirror_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_float,
                                         c_int, c_void_p, c_size_t, c_size_t, c_int, c_int, c_void_p]),
+    "udh_dp_shard_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t,
+                                    c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "udh_debug_x3_materialize": (c_int, [c_void_p, c_size_t, c_int, c_int, POINTER(c_size_t), c_void_p]),
     "udh_debug_x3_set_rows": (c_int, [c_int]),
     "udh_debug_x3_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -101,6 +103,10 @@ SIGNATURES = {
     "udh_launch_count": (c_ulonglong, []),
     "udh_set_sm_reserve": (c_int, [c_int]),
     "udh_set_sm_reserve_top": (c_int, [c_int]),
+    "udh_set_adam_grid": (c_int, [c_int]),
+    "udh_set_bwd_marker": (c_int, [c_int]),
+    "udh_set_sm_reserve_marker": (c_int, [c_int]),
+    "udh_bwd_marker_wait": (c_int, [c_void_p]),
     "udh_prof_enable": (c_int, [c_int]),
     "udh_prof_reset": (c_int, []),
     "udh_prof_num_tags": (c_int, []),

@@ -280,6 +280,7 @@ extern "C" int udh_cnn_bwd_phase(const float* params, const float* I1, const flo
   float* g = gA;
   float* other = gB;
   for (int i = 7; i >= 0; --i) {
+    TRY(bwd_marker_record(i, st));
     const int s = P / kConv[i].div;
     const int cin = kConv[i].cin, cout = kConv[i].cout;
     // layer input: previous conv output, a pool output, or the two input planes

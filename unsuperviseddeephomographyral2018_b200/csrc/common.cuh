@@ -32,6 +32,15 @@ inline int persistent_ctas() {
   const int n = sms - g_sm_reserve;
   return n > 0 ? n : 1;
 }
+extern int g_bwd_marker_layer, g_sm_reserve_marker;   // udh_set_bwd_marker / udh_set_sm_reserve_marker
+// SMs the persistent backward kernels of conv layer i leave free: the global reserve, conv4_x's (udh_set_sm_reserve_top), and
+// from the marker layer down the SMs handed to the second stream's kernel (udh_set_sm_reserve_marker)
+inline int bwd_sm_reserve(int i, int reserve_all) {
+  int r = (i >= 6 && g_sm_reserve_top > reserve_all) ? g_sm_reserve_top : reserve_all;
+  if (g_bwd_marker_layer >= 0 && i <= g_bwd_marker_layer && g_sm_reserve_marker > r) r = g_sm_reserve_marker;
+  return r;
+}
+int bwd_marker_record(int layer, cudaStream_t st);   // udh_set_bwd_marker: event before layer's backward kernels
 void prof_begin(int tag, cudaStream_t st);
 void prof_end(int tag, cudaStream_t st);
 struct ProfScope {

@@ -532,9 +532,10 @@ int x3_cnn_bwd_convs(const float* params, const size_t* poff, const float* I1, c
   const int reserve_all = g_sm_reserve;
   struct RestoreReserve { int v; ~RestoreReserve() { g_sm_reserve = v; } } restore_reserve{reserve_all};
   for (int i = 7; i >= 0; --i) {
+    TRY(bwd_marker_record(i, st));
     const int s = P / kConv[i].div;
     const int cin = kConv[i].cin, cout = kConv[i].cout;
-    g_sm_reserve = (i >= 6 && g_sm_reserve_top > reserve_all) ? g_sm_reserve_top : reserve_all;   // see udh_set_sm_reserve_top
+    g_sm_reserve = bwd_sm_reserve(i, reserve_all);   // see udh_set_sm_reserve_top / udh_set_sm_reserve_marker
     {
       ProfScope ps(PROF_CONV_WGRAD0 + i, st);
       if (i == 0) TRY(conv1_x3_wgrad(I1, I2, U16(tcw, L.G[0]), grads + poff[0], grads + poff[1], B, s, s, st));

@@ -19,6 +19,11 @@ void set_error(const char* fmt, ...) {
 unsigned long long g_launches = 0;
 int g_sm_reserve = 0;
 int g_sm_reserve_top = 0;
+int g_bwd_marker_layer = -1;   // udh_set_bwd_marker
+int g_sm_reserve_marker = 0;    // udh_set_sm_reserve_marker
+static cudaEvent_t g_bwd_marker_ev = nullptr;
+static bool g_bwd_marker_recorded = false;
+int g_adam_grid = 0;        // udh_set_adam_grid: CTAs of the next Adam launches (0 = fill the device)
 
 namespace {
 const char* kTagNames[PROF_NUM_TAGS] = {
@@ -148,6 +153,40 @@ extern "C" int udh_set_sm_reserve(int n) {
   return UDH_OK;
 }
 
+namespace udh {
+int bwd_marker_record(int layer, cudaStream_t st) {
+  if (layer != g_bwd_marker_layer) return UDH_OK;
+  if (!g_bwd_marker_ev) UDH_CUDA(cudaEventCreateWithFlags(&g_bwd_marker_ev, cudaEventDisableTiming));
+  UDH_CUDA(cudaEventRecord(g_bwd_marker_ev, st));
+  g_bwd_marker_recorded = true;
+  return UDH_OK;
+}
+}  // namespace udh
+
+extern "C" int udh_set_bwd_marker(int layer) {
+  UDH_REQUIRE(layer >= -1 && layer <= 7, "udh_set_bwd_marker: layer must be -1 (off) or 0..7");
+  udh::g_bwd_marker_layer = layer;
+  return UDH_OK;
+}
+
+extern "C" int udh_set_sm_reserve_marker(int n) {
+  UDH_REQUIRE(n >= 0 && n < 128, "udh_set_sm_reserve_marker: bad value %d", n);
+  udh::g_sm_reserve_marker = n;
+  return UDH_OK;
+}
+
+extern "C" int udh_bwd_marker_wait(void* stream) {
+  if (!udh::g_bwd_marker_recorded) return UDH_OK;      // nothing recorded yet: no dependency to add
+  UDH_CUDA(cudaStreamWaitEvent(udh::as_stream(stream), udh::g_bwd_marker_ev, 0));
+  return UDH_OK;
+}
+
+extern "C" int udh_set_adam_grid(int blocks) {
+  UDH_REQUIRE(blocks >= 0 && blocks <= 148 * 16, "udh_set_adam_grid: blocks must be in 0..2368");
+  udh::g_adam_grid = blocks;
+  return UDH_OK;
+}
+
 extern "C" int udh_set_sm_reserve_top(int n) {
   UDH_REQUIRE(n >= 0 && n < 128, "udh_set_sm_reserve_top: bad value %d", n);
   udh::g_sm_reserve_top = n;
@@ -217,7 +256,8 @@ extern "C" int udh_adam_step_mirror_ex(float* p, float* g, float* m, float* v, s
   UDH_REQUIRE(((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0, "udh_adam_step: buffers must be 16-byte aligned");
   if (n == 0) return UDH_OK;
   const size_t n4 = n / 4;
-  const unsigned blocks = (unsigned)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  const size_t full = (n4 + 255) / 256, cap = udh::g_adam_grid > 0 ? (size_t)udh::g_adam_grid : (size_t)148 * 16;
+  const unsigned blocks = (unsigned)(full < cap ? full : cap);
   udh::ProfScope ps(udh::PROF_ADAM, udh::as_stream(stream));
   udh::launch_chain(udh::adam_kernel, dim3(blocks), dim3(256), 0, udh::as_stream(stream), (float4*)p, (float4*)g, (float4*)m, (float4*)v, n4, alpha_t,
                                                               beta1, beta2, eps, grad_scale, zero_grad, (uint2*)mirror,

@@ -8,8 +8,10 @@ All arithmetic is in libudh's CUDA kernels; torch provides memory, streams and t
 """
 import ctypes
 import math
+import os
 from collections import OrderedDict
 
+import numpy as np
 import torch
 
 from . import _lib, ops, params as P
@@ -65,8 +67,13 @@ class HomographyEngine(object):
         self.specs = P.param_specs(patch_size)
         n = P.total_floats(self.specs)
         assert n == lib.udh_param_total_floats(patch_size), "python / C parameter layouts disagree"
-        self.params = torch.zeros(n, device=self.device, dtype=torch.float32)
-        self.grads = torch.zeros_like(self.params)
+        self.pg = process_group
+        self.world_size = world_size
+        # N > 1: parameters, gradients and the workspace (it holds fc1's weight mirror) are symmetric-memory allocations bound
+        # to an NVSwitch multicast object when the box offers one (_dp_setup_multicast) — plain device memory otherwise
+        self._symm = self._dp_want_multicast()
+        self.params = self._alloc(n, torch.float32).zero_()
+        self.grads = self._alloc(n, torch.float32).zero_()
         self.adam_m = torch.zeros_like(self.params)
         self.adam_v = torch.zeros_like(self.params)
         if seed is not None:
@@ -74,7 +81,7 @@ class HomographyEngine(object):
         self.ws_bytes = lib.udh_cnn_workspace_bytes(self.B, self.Pz, self.numeric)
         if self.ws_bytes == 0:
             raise _lib.UdhError("unsupported batch / patch size (%d, %d)" % (self.B, self.Pz))
-        self.ws = torch.empty(self.ws_bytes, device=self.device, dtype=torch.uint8)
+        self.ws = self._alloc(self.ws_bytes, torch.uint8)
         check(lib.udh_cnn_workspace_init(self._p(self.ws), self.ws_bytes, self.B, self.Pz, self.numeric, ops._stream()),
               "udh_cnn_workspace_init")
         # bf16 mode: Adam refreshes the bf16 copy of fc1's weights in the same pass, the next forward skips its conversion
@@ -85,14 +92,26 @@ class HomographyEngine(object):
         self._mirror_current = False
         self._mirror_version = -1          # torch version counter of self.params when the mirror was written
         self.global_step = 0
-        self.pg = process_group
-        self.world_size = world_size
-        self._comm_stream = torch.cuda.Stream(device=self.device) if world_size > 1 else None
-        if world_size > 1:
-            import os
-            check(lib.udh_set_sm_reserve(int(os.environ.get("UDH_SM_RESERVE", "0"))), "udh_set_sm_reserve")
-            # the conv4_x backward launches overlap the fc-gradient allreduce: leave NCCL's SMs to it (udh.h)
-            check(lib.udh_set_sm_reserve_top(int(os.environ.get("UDH_SM_RESERVE_TOP", "32"))), "udh_set_sm_reserve_top")
+        self._mv_sharded = False
+        self._mc = self._dp_setup_multicast() if self._symm else None
+        # second stream: Row G of the fully connected slice under the conv backward.  UDH_OVERLAP_UPDATE=1 also moves that
+        # slice's Adam there at N = 1; measured on B200 it gains nothing (whichever conv kernel starts next waits for the
+        # update's CTAs to leave its SMs: profiles/r2_dp_overlap_experiments.md), so it is off by default.
+        self._overlap_update = os.environ.get("UDH_OVERLAP_UPDATE", "0") == "1"
+        self._comm_stream = torch.cuda.Stream(device=self.device) if (world_size > 1 or self._overlap_update) else None
+        # SM policy of this engine's steps (library-global knobs, applied at the start of every step).  A conv CTA with 200+ KB
+        # of shared memory shares its SM with nothing, so a second stream's kernel and the persistent conv kernels take turns
+        # on an SM rather than overlap:
+        #   top: the SMs NCCL's allreduce kernel (NCCL_MAX_CTAS) takes next to conv4_x's backward on the NCCL path — those four
+        #     launches have <= 2 items per CTA and lose nothing on 116 CTAs;
+        #   marker layer / SMs: where in the conv backward the multicast kernel (or UDH_OVERLAP_UPDATE's Adam) starts, and how
+        #     many SMs the conv kernels from there on leave to it (0: it queues for SMs like any other kernel).
+        side_kernel = self._mc is not None or self._overlap_update
+        sms = int(os.environ.get("UDH_DP_SMS", "0")) if side_kernel else 0
+        self._sm_policy = dict(reserve=int(os.environ.get("UDH_SM_RESERVE", "0")) if world_size > 1 else 0,
+                               top=int(os.environ.get("UDH_SM_RESERVE_TOP", "32")) if (world_size > 1 and self._mc is None) else 0,
+                               marker=int(os.environ.get("UDH_DP_MARKER_LAYER", "3")) if side_kernel else -1, marker_sms=sms)
+        self._side_adam_grid = int(os.environ.get("UDH_SIDE_ADAM_GRID", str(sms * 8 if sms else 296)))
         # static per-step outputs of the one-call step (udh_step_forward_backward): reused every step
         B, Pz, dev = self.B, self.Pz, self.device
         self._sb = dict(h4p=torch.zeros(B, 8, device=dev), H=torch.zeros(B, 3, 3, device=dev), pred=torch.zeros(B, Pz, Pz, 1, device=dev),
@@ -206,6 +225,7 @@ class HomographyEngine(object):
     # ------------------------------------------------------------------ backward + update
     def backward(self, batch, out):
         """Gradient of the selected loss into self.grads (which must be zero on entry)."""
+        self._apply_sm_policy()
         lt = self.loss_type
         if lt == "h_loss":
             dpred = out["_dpred"]
@@ -246,21 +266,115 @@ class HomographyEngine(object):
             else:
                 torch.distributed.all_reduce(self.grads, group=self.pg)
 
-    def update(self):
-        t = self.global_step + 1
-        lr_t = learning_rate(self.global_step, self.lr, self.min_lr)
-        alpha = lr_t * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+    # ------------------------------------------------------------------ Row G over NVSwitch multicast memory
+    def _dp_want_multicast(self):
+        """UDH_DP_MODE = nccl (default) | multicast.  `multicast` selects the fused switch-reduce / sharded-Adam / weight-multicast
+        kernel (csrc/dp_update.cu) for fc1's weights; it is parity-tested but measured no faster than the NCCL path on B200
+        (DESIGN.md section 6), hence opt-in."""
+        mode = os.environ.get("UDH_DP_MODE", "nccl")
+        if mode not in ("nccl", "multicast"):
+            raise ValueError("UDH_DP_MODE must be nccl or multicast")
+        if self.world_size <= 1 or mode == "nccl" or self.pg is None:
+            return None
+        import torch.distributed._symmetric_memory as symm
+        return symm
+
+    def _alloc(self, n, dtype):
+        if self._symm is not None:
+            return self._symm.empty(int(n), dtype=dtype, device=self.device)
+        return torch.empty(int(n), device=self.device, dtype=dtype)
+
+    def _dp_setup_multicast(self):
+        """Rendezvous of the three symmetric buffers (collective, same order on every rank).  Returns the multicast addresses
+        and this rank's shard of fc1's weights; fails loudly when the fabric has no multicast support."""
+        symm = self._symm
+        name = self.pg.group_name
+        hp, hg, hw = (symm.rendezvous(t, group=name) for t in (self.params, self.grads, self.ws))
+        mcs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (hp, hg, hw)]
+        if not all(mcs):
+            raise _lib.UdhError("UDH_DP_MODE=multicast: no NVSwitch multicast address for the symmetric buffers")
+        w = self.specs["model/fc1/fc1/weights"]
+        begin, count = w.offset, int(np.prod(w.shape))
+        if self._mirror is not None:
+            mp, mb, mc, stored = self._mirror
+            assert (mb, mc) == (begin, count) and stored, "the sharded update assumes fc1's weight gradient is stored"
+        rank, N = hp.rank, hp.world_size
+        per = -(-count // (4 * N)) * 4                                   # 4-float aligned shards, the last one may be shorter
+        lo = min(begin + rank * per, begin + count)
+        hi = min(lo + per, begin + count)
+        return dict(hp=hp, hg=hg, hw=hw, mc_params=mcs[0], mc_grads=mcs[1], mc_ws=mcs[2], begin=begin, count=count, shard=(lo, hi),
+                    per=per, rank=rank, N=N, grid=int(os.environ.get("UDH_DP_GRID", "0")))
+
+    def _dp_sharded_update(self, alpha):
+        """fc1's weights: udh_dp_shard_update (switch-side gradient sum, Adam on this rank's shard, new weights and limbs
+        multicast to all replicas) -> barrier, on the current (communication) stream; the caller has enqueued the barrier that
+        orders every rank's fc gradients before it."""
+        mc = self._mc
+        lo, hi = mc["shard"]
+        mirror, limbs, mb, mcount = None, 0, 0, 0
+        if self._mirror is not None:
+            mp, mb, mcount, _ = self._mirror
+            mirror = ctypes.c_void_p(mc["mc_ws"] + (mp - self.ws.data_ptr()))
+            limbs = 2 if self.numeric == _lib.NUMERIC_BF16X3 else 1
+        check(lib.udh_dp_shard_update(ctypes.c_void_p(mc["mc_grads"]), self._p(self.params), ctypes.c_void_p(mc["mc_params"]),
+                                      self._p(self.adam_m), self._p(self.adam_v), mirror, lo, hi - lo, mb, mcount, limbs, alpha, 0.9, 0.999,
+                                      1e-8, 1.0 / self.world_size, mc["grid"], ops._stream()), "udh_dp_shard_update")
+        mc["hg"].barrier(channel=1, timeout_ms=30000)                    # every owner's stores have landed in every replica
+        self._mv_sharded = True
+
+    def sync_optimizer_state(self):
+        """COLLECTIVE (all ranks).  With the sharded update each rank holds Adam's m, v of fc1's weights for its own shard only;
+        this gathers them so that every rank's adam_m / adam_v is complete (call it before a rank saves a checkpoint)."""
+        if self._mc is None or not self._mv_sharded:
+            return
+        mc = self._mc
+        for r in range(mc["N"]):
+            lo = min(mc["begin"] + r * mc["per"], mc["begin"] + mc["count"])
+            hi = min(lo + mc["per"], mc["begin"] + mc["count"])
+            if hi > lo:
+                torch.distributed.broadcast(self.adam_m[lo:hi], group=self.pg, group_src=r)
+                torch.distributed.broadcast(self.adam_v[lo:hi], group=self.pg, group_src=r)
+        self._mv_sharded = False
+
+    def _apply_sm_policy(self):
+        pol = self._sm_policy
+        check(lib.udh_set_sm_reserve(pol["reserve"]), "udh_set_sm_reserve")
+        check(lib.udh_set_sm_reserve_top(pol["top"]), "udh_set_sm_reserve_top")
+        check(lib.udh_set_bwd_marker(pol["marker"]), "udh_set_bwd_marker")
+        check(lib.udh_set_sm_reserve_marker(pol["marker_sms"]), "udh_set_sm_reserve_marker")
+
+    def _adam(self, lo, hi, alpha):
+        """TF-1 Adam on the float range [lo, hi) of the flat buffers (4-float aligned), on the current stream; refreshes the
+        part of fc1's tensor-core weight mirror that falls inside the range."""
+        n = hi - lo
+        off = lo * 4
+        pp = lambda t: ctypes.c_void_p(t.data_ptr() + off)
         if self._mirror is not None:
             mp, mb, mc, stored = self._mirror
             limbs = 2 if self.numeric == _lib.NUMERIC_BF16X3 else 1
-            check(lib.udh_adam_step_mirror_ex(self._p(self.params), self._p(self.grads), self._p(self.adam_m), self._p(self.adam_v),
-                                              self.params.numel(), alpha, 0.9, 0.999, 1e-8, 1.0 / self.world_size, 1,
-                                              ctypes.c_void_p(mp), mb, mc, stored, limbs, ops._stream()), "udh_adam_step_mirror_ex")
+            inside = lo <= mb and mb + mc <= hi
+            if not inside and not (mb + mc <= lo or hi <= mb):
+                raise _lib.UdhError("Adam range splits the fc1 mirror")
+            check(lib.udh_adam_step_mirror_ex(pp(self.params), pp(self.grads), pp(self.adam_m), pp(self.adam_v), n, alpha, 0.9, 0.999,
+                                              1e-8, 1.0 / self.world_size, 1, ctypes.c_void_p(mp if inside else None),
+                                              (mb - lo) if inside else 0, mc if inside else 0, stored, limbs, ops._stream()),
+                  "udh_adam_step_mirror_ex")
+        else:
+            check(lib.udh_adam_step(pp(self.params), pp(self.grads), pp(self.adam_m), pp(self.adam_v), n, alpha, 0.9, 0.999, 1e-8,
+                                    1.0 / self.world_size, 1, ops._stream()), "udh_adam_step")
+
+    def _alpha(self):
+        t = self.global_step + 1
+        lr_t = learning_rate(self.global_step, self.lr, self.min_lr)
+        return lr_t, lr_t * math.sqrt(1.0 - 0.999 ** t) / (1.0 - 0.9 ** t)
+
+    def update(self):
+        self.sync_optimizer_state()          # no-op unless sharded steps (train_step on the multicast path) came before
+        lr_t, alpha = self._alpha()
+        self._adam(0, self.params.numel(), alpha)
+        if self._mirror is not None:
             self._mirror_current = True
             self._mirror_version = self.params._version
-        else:
-            ops.adam_step(self.params, self.grads, self.adam_m, self.adam_v, alpha, 0.9, 0.999, 1e-8,
-                          1.0 / self.world_size, zero_grad=True)
         self.global_step += 1
         return lr_t
 
@@ -298,21 +412,60 @@ class HomographyEngine(object):
         the engine's static buffers (valid until the next step)."""
         a = self._fill_args(batch, True)
         st = ops._stream()
-        if self.world_size == 1:
+        self._apply_sm_policy()
+        if self.world_size == 1 and not self._overlap_update:
             check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_ALL, st), "udh_step_forward_backward")
-        else:
-            # Row G with overlap: allreduce the fully connected gradients (134 of 137 MB) under the conv backward
-            cur = torch.cuda.current_stream()
-            check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_FWD_HEAD, st), "udh_step_forward_backward(head)")
-            head, convs = dp_slices(self.specs)
-            self._comm_stream.wait_stream(cur)
-            with torch.cuda.stream(self._comm_stream):
-                torch.distributed.all_reduce(self.grads[head], group=self.pg)
+            out = self._step_out(batch)
+            out["lr"] = self.update()
+            return out
+        # The fully connected gradients (fc1 = 134 of the 137 MB) are final after the head phase of the backward: Row G for them
+        # runs on a second stream underneath the conv backward.
+        cur = torch.cuda.current_stream()
+        side = self._comm_stream
+        lr_t, alpha = self._alpha()
+        head, convs = dp_slices(self.specs)
+        n = self.params.numel()
+        check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_FWD_HEAD, st), "udh_step_forward_backward(head)")
+        side.wait_stream(cur)
+        if self._mc is not None:
+            # multicast path: fc1's weights (98 % of the bytes) are reduced, updated and redistributed by ONE kernel over
+            # NVSwitch multicast memory (csrc/dp_update.cu); the rest (conv layers, biases, fc2: 2.6 MB) goes through NCCL.
+            # The kernel starts at the backward marker (udh_set_bwd_marker): under the wide layers' backward, not conv4_x's.
+            w0, w1 = self._mc["begin"], self._mc["begin"] + self._mc["count"]
+            with torch.cuda.stream(side):
+                torch.distributed.all_reduce(self.grads[w1:], group=self.pg)     # fc1 bias, fc2: final after the head phase too
+                self._adam(w1, n, alpha)
+                self._mc["hg"].barrier(channel=0, timeout_ms=30000)      # every rank's fc gradients are final (and its fc1 reads done)
             check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_CONVS, st), "udh_step_forward_backward(convs)")
-            torch.distributed.all_reduce(self.grads[convs], group=self.pg)
-            cur.wait_stream(self._comm_stream)
+            with torch.cuda.stream(side):
+                check(lib.udh_bwd_marker_wait(ops._stream()), "udh_bwd_marker_wait")
+                self._dp_sharded_update(alpha)
+            torch.distributed.all_reduce(self.grads[:w0], group=self.pg)
+            self._adam(0, w0, alpha)
+        else:
+            if self.world_size > 1:
+                with torch.cuda.stream(side):
+                    torch.distributed.all_reduce(self.grads[head], group=self.pg)
+            check(lib.udh_step_forward_backward(ctypes.byref(a), _lib.STEP_CONVS, st), "udh_step_forward_backward(convs)")
+            if self._overlap_update:
+                with torch.cuda.stream(side):
+                    check(lib.udh_bwd_marker_wait(ops._stream()), "udh_bwd_marker_wait")
+                    check(lib.udh_set_adam_grid(self._side_adam_grid), "udh_set_adam_grid")     # co-resident with the conv CTAs (udh.h)
+                    self._adam(head.start, n, alpha)
+                    check(lib.udh_set_adam_grid(0), "udh_set_adam_grid")
+            if self.world_size > 1:
+                torch.distributed.all_reduce(self.grads[convs], group=self.pg)
+            if self._overlap_update:
+                self._adam(0, head.start, alpha)
+        cur.wait_stream(side)
+        if self._mc is None and not self._overlap_update:
+            self._adam(0, n, alpha)
+        if self._mirror is not None:
+            self._mirror_current = True
+            self._mirror_version = self.params._version
+        self.global_step += 1
         out = self._step_out(batch)
-        out["lr"] = self.update()
+        out["lr"] = lr_t
         return out
 
     def eval_step(self, batch):
