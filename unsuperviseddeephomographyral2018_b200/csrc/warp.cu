@@ -45,16 +45,8 @@ struct Tap {
   float xn, yn, ts;
 };
 
-// Source coordinates of output grid point (xt, yt) in [-1,1] units, reference semantics
-// (tf_spatial_transformer.py:213-240 then _interpolate :97-137).
-__device__ __forceinline__ void sample_setup(const Homog& hm, float xt, float yt, int W, int Hh, Tap& t) {
-  const float xs = fmaf(hm.h[0], xt, fmaf(hm.h[1], yt, hm.h[2]));
-  const float ys = fmaf(hm.h[3], xt, fmaf(hm.h[4], yt, hm.h[5]));
-  float ts = fmaf(hm.h[6], xt, fmaf(hm.h[7], yt, hm.h[8]));
-  if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;                    // smallers = 1e-6 * (1 - [|t| >= 1e-7])
-  const float xn = xs / ts, yn = ys / ts;
-  const float x = (xn + 1.0f) * (float)W / 2.0f;
-  const float y = (yn + 1.0f) * (float)Hh / 2.0f;
+// Clip-then-weight bilinear taps of the source position (x, y) in pixels (tf_spatial_transformer.py:97-137).
+__device__ __forceinline__ void tap_from_xy(float x, float y, int W, int Hh, Tap& t) {
   // floor -> int32 with saturation (far-away samples all clip to the border pixel pair anyway)
   const float xf = fminf(fmaxf(floorf(x), -2.0f), (float)W + 1.0f);
   const float yf = fminf(fmaxf(floorf(y), -2.0f), (float)Hh + 1.0f);
@@ -70,6 +62,20 @@ __device__ __forceinline__ void sample_setup(const Homog& hm, float xt, float yt
   t.wc = __fmul_rn(x - t.x0f, t.y1f - y);
   t.wd = __fmul_rn(x - t.x0f, y - t.y0f);
   t.i00 = y0 * W + x0; t.i01 = y0 * W + x1; t.i10 = y1 * W + x0; t.i11 = y1 * W + x1;
+  t.x = x; t.y = y;
+}
+
+// Source coordinates of output grid point (xt, yt) in [-1,1] units, reference semantics
+// (tf_spatial_transformer.py:213-240 then _interpolate :97-137).
+__device__ __forceinline__ void sample_setup(const Homog& hm, float xt, float yt, int W, int Hh, Tap& t) {
+  const float xs = fmaf(hm.h[0], xt, fmaf(hm.h[1], yt, hm.h[2]));
+  const float ys = fmaf(hm.h[3], xt, fmaf(hm.h[4], yt, hm.h[5]));
+  float ts = fmaf(hm.h[6], xt, fmaf(hm.h[7], yt, hm.h[8]));
+  if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;                    // smallers = 1e-6 * (1 - [|t| >= 1e-7])
+  const float xn = xs / ts, yn = ys / ts;
+  const float x = (xn + 1.0f) * (float)W / 2.0f;
+  const float y = (yn + 1.0f) * (float)Hh / 2.0f;
+  tap_from_xy(x, y, W, Hh, t);
   t.x = x; t.y = y; t.xn = xn; t.yn = yn; t.ts = ts;
 }
 
@@ -117,31 +123,38 @@ __device__ __forceinline__ void window_origin(const int32_t* __restrict__ patch_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// forward: grid (ceil(pw/128) * ceil(ph/32), B), 256 threads; each thread owns 4 consecutive pixels of 4 rows
-// (rows interleaved by 8 so a warp still walks whole 128-pixel row segments: coalesced float4 I2 / pred accesses).
-// In-range samples (the common case) take a branch-free fast path that produces bit-identical weights; samples whose
-// taps clip go through the general reference-exact path.  Reductions: fp32 over the thread's 16 pixels, then fp64.
+// forward: grid (X, B), 256 threads.  A sample's window is a flat list of ph * pw/4 pixel quads (4 consecutive pixels of a
+// row); thread t of CTA x takes quads x*256 + t, + X*256, ...: every warp reads / writes 512 contiguous bytes of I2 / pred
+// per iteration whatever the window width (a 320-wide row is 2.5 warps, no idle lanes), and X is chosen so that B * X CTAs
+// fill the device once (no second, mostly empty wave).
+// In-range samples (the common case) take a fast path; samples whose taps clip go through the general clip-then-weight
+// path.  The choice is made PER WARP (__all_sync): a warp that straddles the image border runs the general path for all of
+// its lanes instead of both paths one after the other — the two produce the same fp32 weights for in-range samples.
+// Reductions: fp32 over the thread's pixels, then fp64.
 // ------------------------------------------------------------------------------------------------------------
 template <int C>
-__device__ __forceinline__ float sample_pixel(const float* __restrict__ img, const Homog& hm, float xt, float yt, float bx, float by,
-                                              float bt, int W, int Hh) {
+__device__ __forceinline__ float sample_pixel(const float* __restrict__ img, const Homog& hm, float xt, float bx, float by, float bt,
+                                              int W, int Hh) {
   const float xs = fmaf(hm.h[0], xt, bx), ys = fmaf(hm.h[3], xt, by);
   float ts = fmaf(hm.h[6], xt, bt);
   if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;
-  // ONE correctly rounded reciprocal instead of two IEEE divisions (the kernel is issue-bound, not DRAM-bound: ncu of round 1):
-  // xs * (1/ts) is within 1.5 ulp of xs / ts, i.e. < 5e-5 px on coordinates of a few hundred px — far inside the parity
-  // tolerance of the warp (2e-4 on 99.9 % of the pixels).  Samples that clip take the reference-exact path below.
-  const float rt = __frcp_rn(ts);
+  // ONE hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions (the kernel is issue-bound, not DRAM-bound: ncu
+  // of round 1; a correctly rounded __frcp_rn costs ~8 instructions, this one 1): xs * (1/ts) is within 2 ulp of xs / ts,
+  // i.e. < 7e-5 px on coordinates of a few hundred px — far inside the parity tolerance of the warp (2e-4 on 99.9 % of the
+  // pixels).  |ts| >= 1e-7 here (epsilon rule above), so the .ftz of the approximation never sees a denormal.
+  float rt;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(ts));
   const float x = (xs * rt + 1.0f) * (float)W * 0.5f;
   const float y = (ys * rt + 1.0f) * (float)Hh * 0.5f;
-  if (x >= 0.0f && x < (float)(W - 1) && y >= 0.0f && y < (float)(Hh - 1)) {
+  const bool inside = x >= 0.0f && x < (float)(W - 1) && y >= 0.0f && y < (float)(Hh - 1);
+  if (__all_sync(0xffffffffu, inside)) {
     // no tap clips: floor == truncation, x1 = x0 + 1 — same fp32 values as the general path
     const int x0 = (int)x, y0 = (int)y;
     const float x0f = (float)x0, y0f = (float)y0;
     const float dx1 = (x0f + 1.0f) - x, dx0 = x - x0f, dy1 = (y0f + 1.0f) - y, dy0 = y - y0f;
     const float wa = __fmul_rn(dx1, dy1), wb = __fmul_rn(dx1, dy0), wc = __fmul_rn(dx0, dy1), wd = __fmul_rn(dx0, dy0);
-    const float* p0 = img + ((size_t)y0 * W + x0) * C;
-    const float* p1 = p0 + (size_t)W * C;
+    const float* p0 = img + (y0 * W + x0) * C;
+    const float* p1 = p0 + W * C;
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
@@ -151,7 +164,7 @@ __device__ __forceinline__ float sample_pixel(const float* __restrict__ img, con
     return C == 1 ? acc : acc / (float)C;
   }
   Tap t;
-  sample_setup(hm, xt, yt, W, Hh, t);
+  tap_from_xy(x, y, W, Hh, t);
   return sample_gray<C>(img, t);
 }
 
@@ -165,9 +178,6 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
   pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ double red[UDH_NSUMS * 32];
   const int b = blockIdx.y;
-  const int tiles_x = (pw + 127) >> 7;
-  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
-  const int c0 = (tx << 7) + ((threadIdx.x & 31) << 2);
   Homog hm;
   normalise_h(H + (size_t)b * 9, img_w, img_h, hm);
   hm.step_x = 2.0f / (float)(img_w - 1);                     // TF LinSpace: step = (stop-start)/(num-1)
@@ -175,42 +185,46 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
   int ox, oy;
   window_origin(patch_indices, idx_stride, b, img_w, ox, oy);
   const float* img = I + (size_t)b * img_h * img_w * C;
+  const int pw4 = pw >> 2, Q = ph * pw4;                     // quads per row / per sample
+  const int stride = gridDim.x * 256;
+  const int dr = stride / pw4, dc = stride - dr * pw4;       // the stride in (row, quad-of-row) steps
+  int q = blockIdx.x * 256 + threadIdx.x;
+  int r = q / pw4, cq = q - r * pw4;
 
   float s_abs = 0.f, s_sq = 0.f, s_hub = 0.f, s_xy = 0.f, s_xx = 0.f, s_yy = 0.f;
-  if (c0 < pw) {
-    float xt[4];
+  // the trip count is warp-uniform (sample_pixel votes across the warp): lanes past the end recompute the last quad, unused
+  for (int q0 = q - (int)(threadIdx.x & 31); q0 < Q; q0 += stride) {
+    const bool live = q < Q;
+    const int rr = live ? r : ph - 1, c0 = (live ? cq : pw4 - 1) << 2;
+    const float yt = fmaf(hm.step_y, (float)(oy + rr), -1.0f);
+    // row-constant parts of T_g = H' . (x_t, y_t, 1): identical to fmaf(h0, xt, fmaf(h1, yt, h2)) etc.
+    const float bx = fmaf(hm.h[1], yt, hm.h[2]), by = fmaf(hm.h[4], yt, hm.h[5]), bt = fmaf(hm.h[7], yt, hm.h[8]);
+    float p[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) xt[k] = fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f);
+    for (int k = 0; k < 4; ++k)
+      p[k] = sample_pixel<C>(img, hm, fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f), bx, by, bt, img_w, img_h);
+    if (live) {
+      const size_t o = ((size_t)b * ph + rr) * pw + c0;
+      if (pred) *reinterpret_cast<float4*>(pred + o) = make_float4(p[0], p[1], p[2], p[3]);
+      if (I2) {
+        const float4 tv = __ldg(reinterpret_cast<const float4*>(I2 + o));
+        const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = (ty << 5) + (i << 3) + (threadIdx.x >> 5);
-      if (r < ph) {
-        const float yt = fmaf(hm.step_y, (float)(oy + r), -1.0f);
-        // row-constant parts of T_g = H' . (x_t, y_t, 1): identical to fmaf(h0, xt, fmaf(h1, yt, h2)) etc.
-        const float bx = fmaf(hm.h[1], yt, hm.h[2]), by = fmaf(hm.h[4], yt, hm.h[5]), bt = fmaf(hm.h[7], yt, hm.h[8]);
-        float p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = sample_pixel<C>(img, hm, xt[k], yt, bx, by, bt, img_w, img_h);
-        const size_t o = ((size_t)b * ph + r) * pw + c0;
-        if (pred) *reinterpret_cast<float4*>(pred + o) = make_float4(p[0], p[1], p[2], p[3]);
-        if (I2) {
-          const float4 tv = __ldg(reinterpret_cast<const float4*>(I2 + o));
-          const float tg[4] = {tv.x, tv.y, tv.z, tv.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float d = p[k] - tg[k], ad = fabsf(d);
-            s_abs += ad;
-            if (ALL) {
-              s_sq = fmaf(d, d, s_sq);
-              s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
-              s_xy = fmaf(p[k], tg[k], s_xy);
-              s_xx = fmaf(p[k], p[k], s_xx);
-              s_yy = fmaf(tg[k], tg[k], s_yy);
-            }
+        for (int k = 0; k < 4; ++k) {
+          const float d = p[k] - tg[k], ad = fabsf(d);
+          s_abs += ad;
+          if (ALL) {
+            s_sq = fmaf(d, d, s_sq);
+            s_hub += ad < 1.0f ? 0.5f * d * d : ad - 0.5f;
+            s_xy = fmaf(p[k], tg[k], s_xy);
+            s_xx = fmaf(p[k], p[k], s_xx);
+            s_yy = fmaf(tg[k], tg[k], s_yy);
           }
         }
       }
     }
+    q += stride; r += dr; cq += dc;
+    if (cq >= pw4) { cq -= pw4; ++r; }
   }
   if (sums && I2) {
     if (ALL) {
@@ -500,7 +514,19 @@ extern "C" int udh_warp_loss_fwd_ex(const float* I, int C, int img_h, int img_w,
   if (rc) return rc;
   UDH_REQUIRE(pred || (I2 && sums), "udh_warp_loss_fwd: nothing to compute (no pred, no I2+sums)");
   if (B == 0) return UDH_OK;
-  dim3 grid(((pw + 127) / 128) * ((ph + 31) / 32), B);
+  // B * X CTAs of 256 threads: one full wave of the device (as many CTAs per SM as the kernel's registers allow) when the work
+  // allows, never more CTAs than quads
+  const int quads = ph * (pw / 4), full = (quads + 255) / 256;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const void* fn = C == 3 ? (all_sums ? (const void*)warp_loss_fwd_kernel<3, true> : (const void*)warp_loss_fwd_kernel<3, false>)
+                          : (all_sums ? (const void*)warp_loss_fwd_kernel<1, true> : (const void*)warp_loss_fwd_kernel<1, false>);
+  int per_sm = 4;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+  int X = (sms * per_sm) / B;
+  X = X < 1 ? 1 : (X > full ? full : X);
+  dim3 grid(X, B);
   ProfScope ps(PROF_WARP_FWD, as_stream(stream));
   if (C == 3 && all_sums)
     launch_chain(warp_loss_fwd_kernel<3, true>, grid, dim3(256), 0, as_stream(stream), I, img_h, img_w, H, I2, patch_indices, idx_stride, pw, ph, pred, sums);
