@@ -13,6 +13,6 @@ Hm = torch.empty(B, 9, device="cuda"); sums = torch.zeros(8, device="cuda", dtyp
 p = lambda t: ctypes.c_void_p(t.data_ptr())
 _lib.check(_lib.lib.udh_dlt_fwd(p(pts), p(hh), p(Hm), B, None), "dlt")
 for i in range(int(sys.argv[1]) if len(sys.argv) > 1 else 8):
-    _lib.check(_lib.lib.udh_warp_loss_fwd(p(src[i % nb]), 1, Hh, W, p(Hm), p(tgt[i % nb]), None, 0, W, Hh, None, p(sums), B, None), "warp")
+    _lib.check(_lib.lib.udh_warp_loss_fwd_ex(p(src[i % nb]), 1, Hh, W, p(Hm), p(tgt[i % nb]), None, 0, W, Hh, None, p(sums), 0, B, None), "warp")
 torch.cuda.synchronize()
 print("l1 =", sums[0].item() / (B * Hh * W))

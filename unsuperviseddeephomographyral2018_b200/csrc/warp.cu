@@ -128,44 +128,78 @@ __device__ __forceinline__ void window_origin(const int32_t* __restrict__ patch_
 // per iteration whatever the window width (a 320-wide row is 2.5 warps, no idle lanes), and X is chosen so that B * X CTAs
 // fill the device once (no second, mostly empty wave).
 // In-range samples (the common case) take a fast path; samples whose taps clip go through the general clip-then-weight
-// path.  The choice is made PER WARP (__all_sync): a warp that straddles the image border runs the general path for all of
-// its lanes instead of both paths one after the other — the two produce the same fp32 weights for in-range samples.
+// path.  The choice is made PER WARP AND QUAD (__all_sync): a warp that straddles the image border runs the general path for
+// all of its lanes instead of both paths one after the other — the two produce the same fp32 weights for in-range samples.
 // Reductions: fp32 over the thread's pixels, then fp64.
 // ------------------------------------------------------------------------------------------------------------
-template <int C>
-__device__ __forceinline__ float sample_pixel(const float* __restrict__ img, const Homog& hm, float xt, float bx, float by, float bt,
-                                              int W, int Hh) {
+// Source position (pixels) of the output grid point with abscissa xt on a row whose constant terms are (bx, by, bt).
+__device__ __forceinline__ void source_xy(const Homog& hm, float xt, float bx, float by, float bt, int W, int Hh, float& x, float& y) {
   const float xs = fmaf(hm.h[0], xt, bx), ys = fmaf(hm.h[3], xt, by);
   float ts = fmaf(hm.h[6], xt, bt);
   if (!(fabsf(ts) >= 1e-7f)) ts += 1e-6f;
-  // ONE hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions (the kernel is issue-bound, not DRAM-bound: ncu
-  // of round 1; a correctly rounded __frcp_rn costs ~8 instructions, this one 1): xs * (1/ts) is within 2 ulp of xs / ts,
+  // ONE hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of two IEEE divisions (the kernel is issue / latency bound, not DRAM
+  // bound; a correctly rounded __frcp_rn costs ~8 instructions, this one 1): xs * (1/ts) is within 2 ulp of xs / ts,
   // i.e. < 7e-5 px on coordinates of a few hundred px — far inside the parity tolerance of the warp (2e-4 on 99.9 % of the
   // pixels).  |ts| >= 1e-7 here (epsilon rule above), so the .ftz of the approximation never sees a denormal.
   float rt;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(ts));
-  const float x = (xs * rt + 1.0f) * (float)W * 0.5f;
-  const float y = (ys * rt + 1.0f) * (float)Hh * 0.5f;
-  const bool inside = x >= 0.0f && x < (float)(W - 1) && y >= 0.0f && y < (float)(Hh - 1);
-  if (__all_sync(0xffffffffu, inside)) {
-    // no tap clips: floor == truncation, x1 = x0 + 1 — same fp32 values as the general path
-    const int x0 = (int)x, y0 = (int)y;
-    const float x0f = (float)x0, y0f = (float)y0;
-    const float dx1 = (x0f + 1.0f) - x, dx0 = x - x0f, dy1 = (y0f + 1.0f) - y, dy0 = y - y0f;
-    const float wa = __fmul_rn(dx1, dy1), wb = __fmul_rn(dx1, dy0), wc = __fmul_rn(dx0, dy1), wd = __fmul_rn(dx0, dy0);
-    const float* p0 = img + (y0 * W + x0) * C;
-    const float* p1 = p0 + W * C;
-    float acc = 0.f;
+  x = (xs * rt + 1.0f) * (float)W * 0.5f;
+  y = (ys * rt + 1.0f) * (float)Hh * 0.5f;
+}
+
+// The four pixels of a quad.  Fast path (no tap of any pixel of the WARP clips: floor == truncation, x1 = x0 + 1 — the same
+// fp32 weights as the general path): all 16 C texel loads of the quad are issued before the first blend.
+template <int C>
+__device__ __forceinline__ void sample_quad(const float* __restrict__ img, const Homog& hm, const float (&xt)[4], float bx, float by,
+                                            float bt, int W, int Hh, float (&out)[4]) {
+  float x[4], y[4];
+  bool inside = true;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float Ia = __ldg(p0 + c), Ic = __ldg(p0 + C + c), Ib = __ldg(p1 + c), Id = __ldg(p1 + C + c);
-      acc = __fadd_rn(acc, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa, Ia), __fmul_rn(wb, Ib)), __fmul_rn(wc, Ic)), __fmul_rn(wd, Id)));
-    }
-    return C == 1 ? acc : acc / (float)C;
+  for (int k = 0; k < 4; ++k) {
+    source_xy(hm, xt[k], bx, by, bt, W, Hh, x[k], y[k]);
+    inside = inside && x[k] >= 0.0f && x[k] < (float)(W - 1) && y[k] >= 0.0f && y[k] < (float)(Hh - 1);
   }
-  Tap t;
-  tap_from_xy(x, y, W, Hh, t);
-  return sample_gray<C>(img, t);
+  if (__all_sync(0xffffffffu, inside)) {
+    float wa[4], wb[4], wc[4], wd[4];
+    const float* p0[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int x0 = (int)x[k], y0 = (int)y[k];
+      const float x0f = (float)x0, y0f = (float)y0;
+      const float dx1 = (x0f + 1.0f) - x[k], dx0 = x[k] - x0f, dy1 = (y0f + 1.0f) - y[k], dy0 = y[k] - y0f;
+      wa[k] = __fmul_rn(dx1, dy1); wb[k] = __fmul_rn(dx1, dy0); wc[k] = __fmul_rn(dx0, dy1); wd[k] = __fmul_rn(dx0, dy0);
+      p0[k] = img + (y0 * W + x0) * C;
+    }
+    if (C == 1) {
+      float Ia[4], Ib[4], Ic[4], Id[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        Ia[k] = __ldg(p0[k]); Ic[k] = __ldg(p0[k] + 1); Ib[k] = __ldg(p0[k] + W); Id[k] = __ldg(p0[k] + W + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        out[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa[k], Ia[k]), __fmul_rn(wb[k], Ib[k])), __fmul_rn(wc[k], Ic[k])), __fmul_rn(wd[k], Id[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float* p1 = p0[k] + W * C;
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float Ia = __ldg(p0[k] + c), Ic = __ldg(p0[k] + C + c), Ib = __ldg(p1 + c), Id = __ldg(p1 + C + c);
+          acc = __fadd_rn(acc, __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(wa[k], Ia), __fmul_rn(wb[k], Ib)), __fmul_rn(wc[k], Ic)), __fmul_rn(wd[k], Id)));
+        }
+        out[k] = acc / (float)C;
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    Tap t;
+    tap_from_xy(x[k], y[k], W, Hh, t);
+    out[k] = sample_gray<C>(img, t);
+  }
 }
 
 // ALL = true: the six reductions every photometric diagnostic needs; false: sum |pred - I2| only (l1_loss)
@@ -177,13 +211,21 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
                                                             double* __restrict__ sums) {
   pdl_wait(); pdl_trigger();   // launched through launch_chain (common.cuh)
   __shared__ double red[UDH_NSUMS * 32];
+  __shared__ Homog hm_s;
+  __shared__ int org_s[2];
   const int b = blockIdx.y;
-  Homog hm;
-  normalise_h(H + (size_t)b * 9, img_w, img_h, hm);
-  hm.step_x = 2.0f / (float)(img_w - 1);                     // TF LinSpace: step = (stop-start)/(num-1)
-  hm.step_y = 2.0f / (float)(img_h - 1);
-  int ox, oy;
-  window_origin(patch_indices, idx_stride, b, img_w, ox, oy);
+  if (threadIdx.x == 0) {
+    // per-sample constants once per CTA (their IEEE divisions are ~200 instructions; a thread only samples ~16 pixels)
+    Homog h0;
+    normalise_h(H + (size_t)b * 9, img_w, img_h, h0);
+    h0.step_x = 2.0f / (float)(img_w - 1);                   // TF LinSpace: step = (stop-start)/(num-1)
+    h0.step_y = 2.0f / (float)(img_h - 1);
+    hm_s = h0;
+    window_origin(patch_indices, idx_stride, b, img_w, org_s[0], org_s[1]);
+  }
+  __syncthreads();
+  const Homog hm = hm_s;
+  const int ox = org_s[0], oy = org_s[1];
   const float* img = I + (size_t)b * img_h * img_w * C;
   const int pw4 = pw >> 2, Q = ph * pw4;                     // quads per row / per sample
   const int stride = gridDim.x * 256;
@@ -192,17 +234,17 @@ __global__ void __launch_bounds__(256) warp_loss_fwd_kernel(const float* __restr
   int r = q / pw4, cq = q - r * pw4;
 
   float s_abs = 0.f, s_sq = 0.f, s_hub = 0.f, s_xy = 0.f, s_xx = 0.f, s_yy = 0.f;
-  // the trip count is warp-uniform (sample_pixel votes across the warp): lanes past the end recompute the last quad, unused
+  // the trip count is warp-uniform (sample_quad votes across the warp): lanes past the end recompute the last quad, unused
   for (int q0 = q - (int)(threadIdx.x & 31); q0 < Q; q0 += stride) {
     const bool live = q < Q;
     const int rr = live ? r : ph - 1, c0 = (live ? cq : pw4 - 1) << 2;
     const float yt = fmaf(hm.step_y, (float)(oy + rr), -1.0f);
     // row-constant parts of T_g = H' . (x_t, y_t, 1): identical to fmaf(h0, xt, fmaf(h1, yt, h2)) etc.
     const float bx = fmaf(hm.h[1], yt, hm.h[2]), by = fmaf(hm.h[4], yt, hm.h[5]), bt = fmaf(hm.h[7], yt, hm.h[8]);
-    float p[4];
+    float p[4], xt[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      p[k] = sample_pixel<C>(img, hm, fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f), bx, by, bt, img_w, img_h);
+    for (int k = 0; k < 4; ++k) xt[k] = fmaf(hm.step_x, (float)(ox + c0 + k), -1.0f);
+    sample_quad<C>(img, hm, xt, bx, by, bt, img_w, img_h, p);
     if (live) {
       const size_t o = ((size_t)b * ph + rr) * pw + c0;
       if (pred) *reinterpret_cast<float4*>(pred + o) = make_float4(p[0], p[1], p[2], p[3]);
