@@ -2,7 +2,8 @@
 // The explicit im2col row of a pixel holds BOTH limbs of its 18 taps:  k = tap*2+plane  -> hi limb,  k + 32 -> lo limb
 // (k = 18: the constant 1 of the wgrad's bias row; it has no lo limb).
 // forward : D = A . W1^T + A[:, 0:32] . W2^T  with W1[co] = [w_hi (k < 18) | w_hi (k - 32 < 18)] and W2[co] = [w_lo | 0]
-//           = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo; the epilogue splits bias + ReLU of the fp32 accumulator into limbs again.
+//           = x_hi.w_hi + x_lo.w_hi + x_hi.w_lo; column 18 carries the constant 1 and the bias limbs as its weight, so the
+//           accumulator already holds conv + bias; the epilogue splits its ReLU into limbs again.
 // wgrad   : D[k][co] += A^T . G_hi + A^T . G_lo ; rows k and k + 32 are added into the same dW row by the epilogue
 //           (x_hi.g + x_lo.g; the extra x_lo.g_lo term is harmless), row 18 is the bias gradient.
 #pragma once
@@ -74,7 +75,9 @@ conv1_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
     for (int h = 0; h < 4; ++h) {
       const int k0 = c * 8 + 2 * h;
       const int kk = c < 4 ? k0 : k0 - 32;  // tap index this column multiplies (hi columns 0.., lo columns 32..)
-      const float f0 = kk < 18 ? __ldg(w + kk * 64 + co) : 0.f, f1 = kk + 1 < 18 ? __ldg(w + (kk + 1) * 64 + co) : 0.f;
+      // tap 18 is the constant-1 column of the im2col row: its "weight" is the bias, added by the MMA (hi.b_hi + hi.b_lo)
+      const float f0 = kk < 18 ? __ldg(w + kk * 64 + co) : (kk == 18 ? __ldg(bias + co) : 0.f);
+      const float f1 = kk + 1 < 18 ? __ldg(w + (kk + 1) * 64 + co) : (kk + 1 == 18 ? __ldg(bias + co) : 0.f);
       uint32_t hi, lo;
       split2<FMT>(f0, f1, hi, lo);
       p1[h] = hi;
@@ -113,7 +116,7 @@ conv1_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
         const int n = row / g.H, y = row - n * g.H;
         const int b = i & 1;
         mbar_wait(&a_empty[b], ((i >> 1) & 1) ^ 1);
-        build_im2col_row_x3<FMT>(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, false);
+        build_im2col_row_x3<FMT>(sA + b * 16384, px, I1, I2, n, y, seg * 128 + px, g.H, g.W, true);
         fence_proxy_async();
         mbar_arrive(&a_full[b]);
       }
@@ -132,15 +135,14 @@ conv1_x3_fwd_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv1Geom g
         for (int c = 0; c < 2; ++c) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(b * 64 + c * 32), v);
-#pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c * 32 + k));
-            v[k] = fmaxf(v[k] + bv.x, 0.f); v[k + 1] = fmaxf(v[k + 1] + bv.y, 0.f);
-            v[k + 2] = fmaxf(v[k + 2] + bv.z, 0.f); v[k + 3] = fmaxf(v[k + 3] + bv.w, 0.f);
-          }
+          // the bias arrived through the constant-1 column; ReLU, then the mask bit of channel k = [v > 0] = the sign of
+          // (0 - bits(v)) for v >= +0, shifted in from the top (one negate + one funnel shift per channel)
           uint32_t mw = 0;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mw |= (v[k] > 0.f ? 1u : 0u) << k;
+          for (int k = 31; k >= 0; --k) {
+            v[k] = fmaxf(v[k], 0.f);
+            mw = __funnelshift_l((uint32_t)(-__float_as_int(v[k])), mw, 1);
+          }
           mo[c] = mw;
 #pragma unroll
           for (int k = 0; k < 16; ++k) split2<FMT>(v[2 * k], v[2 * k + 1], hi[c][k], lo[c][k]);
