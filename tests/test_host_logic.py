@@ -90,6 +90,15 @@ def test_data_parallel_contract_gloo_world2(tmp_path):
         tot = float(sum(range(1, world + 1)))
         assert seen == [tot], seen                                     # the head slice was already reduced when the hook ran
         assert float(flat[1]) == tot and float(flat[-1]) == tot and float(flat[specs["model/conv_block1/conv1/weights"].offset]) == 10.0 * tot
+        # the sharded schedule of the multicast path (csrc/dp_update.cu): sum over ranks, Adam on this rank's shard only,
+        # updated shards back to every replica == the replicated update (the shard table is engine.dp_shard_range)
+        lo, hi, per = en.dp_shard_range(0, 1000, rank, world)
+        gs = tower[rank].clone(); dist.all_reduce(gs)
+        shard_p, _, _ = O.adam_step(p[lo:hi], gs[lo:hi] * (1.0 / world), m[lo:hi], v[lo:hi], 1, 1e-3)
+        full_p = torch.zeros(per * world)
+        pad = torch.zeros(per); pad[:hi - lo] = shard_p
+        dist.all_gather(list(full_p.view(world, per).unbind(0)), pad)
+        assert torch.equal(full_p[:1000], mine), (full_p[:1000] - mine).abs().max()
         # per-rank batch sharding as tf.split(batch, num_gpus) (homography_CNN_synthetic.py:199-207)
         full = torch.arange(8)
         assert torch.equal(full.chunk(world)[rank], full[rank * 4:(rank + 1) * 4])
@@ -100,6 +109,25 @@ def test_data_parallel_contract_gloo_world2(tmp_path):
                         "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_dp_shard_table():
+    """engine.dp_shard_range: 4-float aligned shards that cover the tensor exactly once, for even and ragged splits."""
+    pytest.importorskip("torch")
+    from unsuperviseddeephomographyral2018_b200 import engine as en, params as P
+    w = P.param_specs()["model/fc1/fc1/weights"]
+    cases = [(w.offset, int(np.prod(w.shape)), n) for n in (1, 2, 3, 4, 8)] + [(64, 1000, 3), (0, 4, 8), (128, 36, 5)]
+    for begin, count, world in cases:
+        cover = np.zeros(begin + count + 8, np.int32)
+        sizes = []
+        for r in range(world):
+            lo, hi, per = en.dp_shard_range(begin, count, r, world)
+            assert begin <= lo <= hi <= begin + count and lo % 4 == 0 and per % 4 == 0 and hi - lo <= per
+            assert (hi - lo) % 4 == 0 or hi == begin + count
+            cover[lo:hi] += 1
+            sizes.append(hi - lo)
+        assert (cover[begin:begin + count] == 1).all() and cover.sum() == count
+        assert sizes == sorted(sizes, reverse=True)            # full shards first, the ragged / empty ones at the tail
 
 
 def test_named_checkpoint_roundtrip(tmp_path):

@@ -41,6 +41,16 @@ def dp_slices(specs):
     return slice(off, None), slice(0, off)
 
 
+def dp_shard_range(begin, count, rank, world):
+    """Rank `rank`'s contiguous shard [lo, hi) of the float range [begin, begin + count) for the sharded optimiser of the
+    multicast path (csrc/dp_update.cu): 4-float aligned (the kernel moves float4), equal sizes except a shorter / empty tail,
+    together the shards cover the range exactly once.  Returns (lo, hi, per) with `per` the full shard size."""
+    per = -(-count // (4 * world)) * 4
+    lo = min(begin + rank * per, begin + count)
+    hi = min(lo + per, begin + count)
+    return lo, hi, per
+
+
 def allreduce_two_phase(flat, specs, group=None, between=None):
     """sum-allreduce of the flat gradient in the engine's two phases (head slice first, `between()` — the conv backward in
     the engine — then the conv slice).  Device-agnostic: the gloo CPU test drives exactly this function."""
@@ -299,9 +309,7 @@ class HomographyEngine(object):
             mp, mb, mc, stored = self._mirror
             assert (mb, mc) == (begin, count) and stored, "the sharded update assumes fc1's weight gradient is stored"
         rank, N = hp.rank, hp.world_size
-        per = -(-count // (4 * N)) * 4                                   # 4-float aligned shards, the last one may be shorter
-        lo = min(begin + rank * per, begin + count)
-        hi = min(lo + per, begin + count)
+        lo, hi, per = dp_shard_range(begin, count, rank, N)
         return dict(hp=hp, hg=hg, hw=hw, mc_params=mcs[0], mc_grads=mcs[1], mc_ws=mcs[2], begin=begin, count=count, shard=(lo, hi),
                     per=per, rank=rank, N=N, grid=int(os.environ.get("UDH_DP_GRID", "0")))
 
@@ -329,8 +337,7 @@ class HomographyEngine(object):
             return
         mc = self._mc
         for r in range(mc["N"]):
-            lo = min(mc["begin"] + r * mc["per"], mc["begin"] + mc["count"])
-            hi = min(lo + mc["per"], mc["begin"] + mc["count"])
+            lo, hi, _ = dp_shard_range(mc["begin"], mc["count"], r, mc["N"])
             if hi > lo:
                 torch.distributed.broadcast(self.adam_m[lo:hi], group=self.pg, group_src=r)
                 torch.distributed.broadcast(self.adam_v[lo:hi], group=self.pg, group_src=r)
