@@ -166,7 +166,7 @@ def train(args):
                 syn.save(eng, save_args, step)
     eng.sync_optimizer_state()
     if rank == 0:
-        syn.save(eng, save_args, step)
+        syn.save(eng, save_args, step, background=False)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -132,11 +132,36 @@ def restore(eng, ck, kind, reset_step=False):
         eng.load_state_dict(torch.load(ck, map_location="cpu"), reset_step=reset_step)
 
 
-def save(eng, args, step):
+_save_thread = None
+
+
+def wait_for_save():
+    """Join the checkpoint writer of the previous save() (call before exiting or before reading model_dir)."""
+    global _save_thread
+    if _save_thread is not None:
+        _save_thread.join()
+        _save_thread = None
+
+
+def save(eng, args, step, background=True):
+    """train_saver.save(sess, model_dir + model_name, global_step) (:360).  The state is copied to the host here; the 410 MB
+    bundle (parameters + Adam slots) is encoded and written by a thread while training continues."""
+    global _save_thread
+    import threading
     from unsuperviseddeephomographyral2018_b200 import tf_checkpoint as tfc
     prefix = os.path.join(args.model_dir, "%s-%d" % (args.model_name, step))
-    eng.save_tf_checkpoint(prefix)
-    tfc.update_checkpoint_state(args.model_dir, prefix, keep=5)                 # Saver(max_to_keep=5), :303
+    wait_for_save()
+    variables = eng.snapshot_tf_variables()
+
+    def write():
+        tfc.write_checkpoint(prefix, variables)
+        tfc.update_checkpoint_state(args.model_dir, prefix, keep=5)             # Saver(max_to_keep=5), :303
+
+    if background:
+        _save_thread = threading.Thread(target=write, name="udh-checkpoint-writer")
+        _save_thread.start()
+    else:
+        write()
 
 
 def dist_env():
@@ -228,7 +253,7 @@ def train(args):
                 save(eng, args, step)
     eng.sync_optimizer_state()
     if rank == 0:
-        save(eng, args, step)                                           # :389
+        save(eng, args, step, background=False)                         # :389
     if world > 1:
         torch.distributed.destroy_process_group()
 

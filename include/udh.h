@@ -292,6 +292,10 @@ int udh_dp_shard_update(const void* mc_grads, const float* params, void* mc_para
                         void* mc_mirror, size_t shard_begin, size_t shard_count, size_t mirror_begin, size_t mirror_count,
                         int mirror_limbs, float alpha_t, float beta1, float beta2, float eps, float grad_scale, int grid,
                         void* stream);
+/* HOST function (no device work): CRC-32C (Castagnoli) of n bytes, continuing from `crc` (0 to start) — the checksum of
+ * TensorFlow checkpoint V2 bundles (tf.train.Saver, code/homography_CNN_synthetic.py:303,360), which tf_checkpoint.py writes
+ * and verifies.  Hardware crc32 instruction when the CPU has SSE4.2, slicing-by-8 otherwise. */
+uint32_t udh_crc32c(const void* data, size_t n, uint32_t crc);
 int udh_prof_enable(int on);
 int udh_prof_reset(void);
 int udh_prof_num_tags(void);

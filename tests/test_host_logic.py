@@ -130,6 +130,25 @@ def test_dp_shard_table():
         assert sizes == sorted(sizes, reverse=True)            # full shards first, the ragged / empty ones at the tail
 
 
+def test_crc32c_native_and_numpy_agree():
+    """udh_crc32c (C ABI, hardware crc32 / slicing-by-8) against the pure numpy CRC-32C and the standard check value."""
+    from unsuperviseddeephomographyral2018_b200 import _lib, tf_checkpoint as tfc
+    import ctypes
+    assert tfc.crc32c_numpy(b"123456789") == 0xE3069283 and tfc.crc32c(b"123456789") == 0xE3069283
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 8, 9, 63, 4097, 65535, 65536, (1 << 18) + 5):
+        a = rng.integers(0, 256, n + 3, dtype=np.uint8)
+        for off in (0, 3):                                     # aligned and unaligned starts
+            b = a[off:off + n]
+            nat = int(_lib.lib.udh_crc32c(ctypes.c_void_p(b.ctypes.data), b.size, 0))
+            assert nat == tfc.crc32c_numpy(np.ascontiguousarray(b)) == tfc.crc32c(b), (n, off)
+    # continuation: crc(a || b) from crc(a)
+    a = rng.integers(0, 256, 1000, dtype=np.uint8)
+    c1 = int(_lib.lib.udh_crc32c(ctypes.c_void_p(a.ctypes.data), 400, 0))
+    c2 = int(_lib.lib.udh_crc32c(ctypes.c_void_p(a.ctypes.data + 400), 600, c1))
+    assert c2 == tfc.crc32c_numpy(a)
+
+
 def test_named_checkpoint_roundtrip(tmp_path):
     """TF-Slim variable names / shapes: export -> import is lossless, wrong shapes are rejected."""
     from unsuperviseddeephomographyral2018_b200 import params as P

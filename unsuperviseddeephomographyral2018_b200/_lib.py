@@ -2,7 +2,7 @@
 and if that is impossible the import fails loudly."""
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_ulonglong, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint32, c_uint64, c_ulonglong, c_void_p
 
 from . import build_ext
 
@@ -104,6 +104,7 @@ SIGNATURES = {
     "udh_set_sm_reserve": (c_int, [c_int]),
     "udh_set_sm_reserve_top": (c_int, [c_int]),
     "udh_set_adam_grid": (c_int, [c_int]),
+    "udh_crc32c": (c_uint32, [c_void_p, c_size_t, c_uint32]),
     "udh_set_bwd_marker": (c_int, [c_int]),
     "udh_set_sm_reserve_marker": (c_int, [c_int]),
     "udh_bwd_marker_wait": (c_int, [c_void_p]),

@@ -164,9 +164,15 @@ class HomographyEngine(object):
         """TensorFlow checkpoint V2 bundle (<prefix>.index / .data-00000-of-00001) with the reference graph's variable names,
         Adam slots and global_step — what tf.train.Saver writes at code/homography_CNN_synthetic.py:360 (tf_checkpoint.py)."""
         from . import tf_checkpoint as tfc
+        tfc.write_checkpoint(prefix, self.snapshot_tf_variables(with_optimizer))
+
+    def snapshot_tf_variables(self, with_optimizer=True):
+        """Host copy of the state as the name -> array table tf_checkpoint.write_checkpoint takes (the D2H copies happen here;
+        the table can then be written by another thread while training goes on)."""
+        from . import tf_checkpoint as tfc
         m = self.adam_m.cpu().numpy() if with_optimizer else None
         v = self.adam_v.cpu().numpy() if with_optimizer else None
-        tfc.write_checkpoint(prefix, tfc.engine_state_to_variables(self.params.cpu().numpy(), m, v, self.global_step, self.specs))
+        return tfc.engine_state_to_variables(self.params.cpu().numpy(), m, v, self.global_step, self.specs)
 
     def load_tf_checkpoint(self, prefix, reset_step=False):
         """Restore from a TensorFlow checkpoint V2 bundle (e.g. the reference's published models): parameters, and Adam slots /
