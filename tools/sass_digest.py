@@ -15,13 +15,13 @@ for ln in out.splitlines():
     m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z][A-Z0-9_]*)", ln)
     if m and fn:
         per[fn][m.group(1)] += 1; tot[m.group(1)] += 1
-keys = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "HGMMA", "FFMA", "REDG", "ELECT"]
+keys = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "HMMA", "HGMMA", "FFMA", "REDG", "ELECT", "LDGMC"]
 L = ["# SASS instruction digest of the in-tree libudh.so", "",
      "Command: `python tools/sass_digest.py` (= `cuobjdump -sass unsuperviseddeephomographyral2018_b200/libudh.so`, the library",
      "`__graft_entry__.build()` produces with `nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo`); md5 of the binary at digest",
      "time: `%s`." % hashlib.md5(open(so, "rb").read()).hexdigest(), "",
      "Blackwell-native evidence (B200_PROFILING.md): `UTCHMMA` = tcgen05.mma, `UTMALDG` / `UTMASTG` = TMA load / store, `LDTM` = tcgen05.ld,",
-     "`UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops.  No `HMMA` (legacy mma.sync) and no `HGMMA` (Hopper wgmma) anywhere.  The product",
+     "`UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `LDGMC` = multimem.ld_reduce (NVSwitch multicast load-reduce, csrc/dp_update.cu).  No `HMMA` (legacy mma.sync) and no `HGMMA` (Hopper wgmma) anywhere.  The product",
      "library carries no probe kernels (those are in libudh_probe.so).", "",
      "| mnemonic | whole library |", "|---|---|"]
 L += ["| %s | %d |" % (k, tot.get(k, 0)) for k in keys]
