@@ -149,6 +149,43 @@ def test_crc32c_native_and_numpy_agree():
     assert c2 == tfc.crc32c_numpy(a)
 
 
+def test_cli_background_checkpoint_writer(tmp_path):
+    """homography_CNN_synthetic.save(): the state is snapshotted in the caller, the bundle is written by a thread; a second
+    save joins the first, wait_for_save() leaves complete, readable bundles and an up-to-date `checkpoint` state file."""
+    sys.path.insert(0, ROOT)
+    import types
+    import homography_CNN_synthetic as cli
+    from unsuperviseddeephomographyral2018_b200 import params as P, tf_checkpoint as tfc
+    specs = P.param_specs()
+    n = P.total_floats(specs)
+
+    class Eng(object):                                          # the two members save() touches
+        def __init__(self):
+            self.global_step = 0
+            self.calls = 0
+
+        def snapshot_tf_variables(self, with_optimizer=True):
+            self.calls += 1
+            flat = np.full(n, float(self.global_step), np.float32)
+            return tfc.engine_state_to_variables(flat, None, None, self.global_step, specs)
+
+    args = types.SimpleNamespace(model_dir=str(tmp_path), model_name="model.ckpt")
+    eng = Eng()
+    for step in (1000, 2000):
+        eng.global_step = step
+        cli.save(eng, args, step)                               # returns while the writer thread runs
+    cli.wait_for_save()
+    assert eng.calls == 2 and cli._save_thread is None
+    assert tfc.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-2000")
+    for step in (1000, 2000):
+        back = tfc.read_checkpoint(os.path.join(str(tmp_path), "model.ckpt-%d" % step))      # verifies every CRC
+        assert int(np.asarray(back["Variable"]).reshape(-1)[0]) == step      # global_step is the unnamed `Variable` of the graph
+        assert float(back["model/fc2/fc2/biases"][0]) == float(step)
+    eng.global_step = 3000
+    cli.save(eng, args, 3000, background=False)
+    assert tfc.latest_checkpoint(str(tmp_path)).endswith("model.ckpt-3000") and cli._save_thread is None
+
+
 def test_named_checkpoint_roundtrip(tmp_path):
     """TF-Slim variable names / shapes: export -> import is lossless, wrong shapes are rejected."""
     from unsuperviseddeephomographyral2018_b200 import params as P
