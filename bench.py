@@ -345,7 +345,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
         "ms_per_step_ranks": [round(x, 4) for x in ms_ranks], "dp_diag": args.dp_diag or None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "parity": parity,
-        "config": {"workload": "1-GPU train: synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s (BASELINE configs[1])" % args.loss_type,
+        "config": {"workload": ("1-GPU train" if world == 1 else "%d-GPU data-parallel train (batch 128 per GPU)" % world) +
+                               ": synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s (BASELINE configs[1])" % args.loss_type,
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world, "numeric_mode": numeric,
                    "dropout": "on (keep 0.5)", "optimizer": "TF-Adam lr 5e-4 staircase",
                    "l2_policy": "inputs larger than L2: %d rotating batches, 135 MB of inputs + ~1.7 GB of activations touched per step (L2 = 126 MB)" % nb},
