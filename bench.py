@@ -137,6 +137,11 @@ def cpu_oracle_pairs_per_s(sample_b, steps, warmup, loss_type):
     return sample_b * len(times) / tot, tot / len(times) * 1e3, torch.get_num_threads()
 
 
+def workload(loss_type):
+    """The same string in both arms (the driver compares the arms' configs)."""
+    return "train step (BASELINE configs[1]): synthetic rho=45, 128x128 2-ch patches, batch 128 per GPU, loss_type=%s" % loss_type
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -147,7 +152,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "1-GPU train: synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s" % args.loss_type,
+        "config": {"workload": workload(args.loss_type),
                    "sample": "each step = %d pairs of the 128-pair batch on the host CPU" % sample_b},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": "%d pairs/step x %d steps, oracle/ (PyTorch-CPU fp32 restatement; the TF1 reference cannot be installed here)" % (sample_b, steps)},
@@ -345,8 +350,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
         "ms_per_step_ranks": [round(x, 4) for x in ms_ranks], "dp_diag": args.dp_diag or None,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "parity": parity,
-        "config": {"workload": ("1-GPU train" if world == 1 else "%d-GPU data-parallel train (batch 128 per GPU)" % world) +
-                               ": synthetic rho=45, 128x128 2-ch patches, batch 128, loss_type=%s (BASELINE configs[1])" % args.loss_type,
+        "config": {"workload": workload(args.loss_type),
                    "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world, "numeric_mode": numeric,
                    "dropout": "on (keep 0.5)", "optimizer": "TF-Adam lr 5e-4 staircase",
                    "l2_policy": "inputs larger than L2: %d rotating batches, 135 MB of inputs + ~1.7 GB of activations touched per step (L2 = 126 MB)" % nb},
