@@ -84,43 +84,54 @@ def main():
     gm = e2.adam_m.abs()
     sel = gm > 1e-3 * gm.max()
     res["dp_step_vs_manual_max_update_diff_over_lr"] = float((upd1 - upd2)[sel].abs().max() / 5e-4)
-    # ---- (4) the multicast path (switch-side sum, sharded Adam, multicast weights) against the NCCL path, three steps each
+    # ---- (4) the multicast path (switch-side sum, sharded Adam, multicast weights) against the NCCL path, three steps each.
+    # The mode is opt-in and needs NVSwitch multicast memory: a box without it reports that instead of failing the suite.
     e3 = en.HomographyEngine(B, numeric=numeric, seed=None, loss_type="h_loss", lr=5e-4, process_group=pg, world_size=world); e3.load_flat(flat)
-    os.environ["UDH_DP_MODE"] = "multicast"
-    e4 = en.HomographyEngine(B, numeric=numeric, seed=None, loss_type="h_loss", lr=5e-4, process_group=pg, world_size=world); e4.load_flat(flat)
-    os.environ.pop("UDH_DP_MODE")
-    e4.dropout_seed = e3.dropout_seed
-    for i in range(3):
-        bb = synthetic.make_batch(B, seed=500 + 10 * rank + i)
-        e3.train_step(bb); e4.train_step(bb)
-    torch.cuda.synchronize()
     res["nccl_engine_is_nccl"] = e3._mc is None
-    res["multicast_path"] = e4._mc is not None
-    # Adam's m, v of fc1's weights are sharded on the multicast path: after the gather every rank holds all of them
-    e4.sync_optimizer_state()
-    mm = e4.adam_m.clone(); mr = mm.clone(); dist.broadcast(mr, 0)
-    same = torch.tensor([1.0 if torch.equal(mr, mm) else 0.0], device="cuda")
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    res["adam_m_identical_after_sync"] = bool(same.item() == 1.0)
-    w = e4.specs["model/fc1/fc1/weights"]
-    cnt = 1
-    for d_ in w.shape:
-        cnt *= int(d_)
-    per = -(-cnt // (4 * world)) * 4
-    res["adam_m_fc1_nonzero_fraction_per_shard"] = [float((mm[w.offset + r * per:min(w.offset + (r + 1) * per, w.offset + cnt)].abs() > 0).float().mean())
-                                                    for r in range(world)]
-    mine4 = e4.params.clone(); root4 = mine4.clone(); dist.broadcast(root4, 0)
-    same = torch.tensor([1.0 if torch.equal(root4, mine4) else 0.0], device="cuda")
-    dist.all_reduce(same, op=dist.ReduceOp.MIN)
-    res["multicast_params_bit_identical_across_ranks"] = bool(same.item() == 1.0)
-    d = (e3.params - e4.params).abs()
-    res["multicast_vs_nccl_max_param_diff_over_lr"] = float(d.max() / 5e-4)
-    res["multicast_vs_nccl_rel_l2_of_update"] = rel(e4.params - torch.tensor(flat, device="cuda"), e3.params - torch.tensor(flat, device="cuda"))
-    if e4._mirror is not None:                       # the replicas' tensor-core limbs follow the fp32 master
-        mp, mb, mcnt, _ = e4._mirror
-        off = mp - e4.ws.data_ptr()
-        planes = e4.ws[off:off + mcnt * (4 if numeric == "bf16x3" else 2)].view(torch.bfloat16).view(-1, mcnt).float()
-        res["mirror_matches_master"] = rel(planes.sum(0), e4.params[mb:mb + mcnt]) < (1e-4 if numeric == "bf16x3" else 1e-2)
+    os.environ["UDH_DP_MODE"] = "multicast"
+    e4, why = None, ""
+    try:
+        e4 = en.HomographyEngine(B, numeric=numeric, seed=None, loss_type="h_loss", lr=5e-4, process_group=pg, world_size=world)
+    except Exception as e:                                    # symmetric memory / multicast not available here
+        why = "%s: %s" % (type(e).__name__, e)
+    os.environ.pop("UDH_DP_MODE")
+    ok = torch.tensor([1.0 if e4 is not None and e4._mc is not None else 0.0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)                # all ranks take the same branch
+    res["multicast_path"] = bool(ok.item() == 1.0)
+    if not res["multicast_path"]:
+        res["multicast_unavailable"] = why[:300]
+    else:
+        e4.load_flat(flat)
+        e4.dropout_seed = e3.dropout_seed
+        for i in range(3):
+            bb = synthetic.make_batch(B, seed=500 + 10 * rank + i)
+            e3.train_step(bb); e4.train_step(bb)
+        torch.cuda.synchronize()
+        # Adam's m, v of fc1's weights are sharded on the multicast path: after the gather every rank holds all of them
+        e4.sync_optimizer_state()
+        mm = e4.adam_m.clone(); mr = mm.clone(); dist.broadcast(mr, 0)
+        same = torch.tensor([1.0 if torch.equal(mr, mm) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        res["adam_m_identical_after_sync"] = bool(same.item() == 1.0)
+        w = e4.specs["model/fc1/fc1/weights"]
+        cnt = 1
+        for d_ in w.shape:
+            cnt *= int(d_)
+        per = -(-cnt // (4 * world)) * 4
+        res["adam_m_fc1_nonzero_fraction_per_shard"] = [float((mm[w.offset + r * per:min(w.offset + (r + 1) * per, w.offset + cnt)].abs() > 0).float().mean())
+                                                        for r in range(world)]
+        mine4 = e4.params.clone(); root4 = mine4.clone(); dist.broadcast(root4, 0)
+        same = torch.tensor([1.0 if torch.equal(root4, mine4) else 0.0], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        res["multicast_params_bit_identical_across_ranks"] = bool(same.item() == 1.0)
+        d = (e3.params - e4.params).abs()
+        res["multicast_vs_nccl_max_param_diff_over_lr"] = float(d.max() / 5e-4)
+        res["multicast_vs_nccl_rel_l2_of_update"] = rel(e4.params - torch.tensor(flat, device="cuda"), e3.params - torch.tensor(flat, device="cuda"))
+        if e4._mirror is not None:                       # the replicas' tensor-core limbs follow the fp32 master
+            mp, mb, mcnt, _ = e4._mirror
+            off = mp - e4.ws.data_ptr()
+            planes = e4.ws[off:off + mcnt * (4 if numeric == "bf16x3" else 2)].view(torch.bfloat16).view(-1, mcnt).float()
+            res["mirror_matches_master"] = rel(planes.sum(0), e4.params[mb:mb + mcnt]) < (1e-4 if numeric == "bf16x3" else 1e-2)
     if rank == 0:
         with open(out_path, "w") as f:
             json.dump(res, f)
