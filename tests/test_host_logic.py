@@ -111,6 +111,19 @@ def test_data_parallel_contract_gloo_world2(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+def test_no_undefined_names_in_gpu_only_code():
+    """Most of the package only runs on a GPU box; a forgotten import there costs a GPU round trip.  tools/undef_check.py
+    flags names that are loaded but bound nowhere in their module."""
+    import glob
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import undef_check
+    files = (glob.glob(os.path.join(ROOT, "unsuperviseddeephomographyral2018_b200", "*.py")) + glob.glob(os.path.join(ROOT, "*.py")) +
+             glob.glob(os.path.join(ROOT, "tests", "*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "oracle", "*.py")))
+    assert len(files) > 30
+    bad = [(os.path.relpath(f, ROOT), u) for f in files for u in undef_check.undefined_names(f)]
+    assert not bad, bad
+
+
 def test_dp_shard_table():
     """engine.dp_shard_range: 4-float aligned shards that cover the tensor exactly once, for even and ragged splits."""
     pytest.importorskip("torch")
